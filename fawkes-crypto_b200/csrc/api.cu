@@ -1,0 +1,539 @@
+// C ABI of libfawkes_b200.so -- see include/fawkes_b200.h for the reference interfaces
+// each entry point replaces.
+#include "../../include/fawkes_b200.h"
+
+#include <chrono>
+#include <cstring>
+
+#include "internal.h"
+
+namespace fb {
+const char* last_error_cstr();
+
+static uint32_t be32(const uint8_t* p) {
+  return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+int parse_params(const uint8_t* b, size_t len, ParamsView& v) {
+  size_t pos = 0;
+  auto take = [&](size_t n) -> const uint8_t* {
+    if (pos + n > len) return nullptr;
+    const uint8_t* p = b + pos;
+    pos += n;
+    return p;
+  };
+  if (!(v.alpha_g1 = take(64)) || !(v.beta_g1 = take(64)) || !(v.beta_g2 = take(128)) ||
+      !(v.gamma_g2 = take(128)) || !(v.delta_g1 = take(64)) || !(v.delta_g2 = take(128))) {
+    set_error("Parameters truncated in verifying key");
+    return FB_ERR_FORMAT;
+  }
+  struct { const uint8_t** p; uint32_t* n; size_t sz; } secs[6] = {
+      {&v.ic, &v.n_ic, 64}, {&v.h, &v.n_h, 64}, {&v.l, &v.n_l, 64},
+      {&v.a, &v.n_a, 64},   {&v.b1, &v.n_b1, 64}, {&v.b2, &v.n_b2, 128}};
+  for (auto& s : secs) {
+    const uint8_t* q = take(4);
+    if (!q) { set_error("Parameters truncated at a length field"); return FB_ERR_FORMAT; }
+    *s.n = be32(q);
+    if (!(*s.p = take((size_t)*s.n * s.sz))) {
+      set_error("Parameters truncated inside a query (%u points announced)", *s.n);
+      return FB_ERR_FORMAT;
+    }
+  }
+  return FB_OK;
+}
+
+__global__ void k_gather_bitrev(G1Affine* __restrict__ dst, const G1Affine* __restrict__ src, int k,
+                                uint32_t lo, uint32_t cnt) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    uint32_t pos = lo + i;
+    uint32_t r = __brev(pos) >> (32 - k);
+    dst[i] = src[r];
+  }
+}
+
+static void pk_release(ProvingKey* pk) {
+  if (!pk) return;
+  cudaFree(pk->h); cudaFree(pk->l); cudaFree(pk->a); cudaFree(pk->b1); cudaFree(pk->b2);
+  cudaFree(pk->a_map); cudaFree(pk->b_map);
+  free_csr(pk->csr);
+  pk->dom.destroy();
+  cudaFree(pk->w);
+  for (int i = 0; i < 3; i++) cudaFree(pk->ev[i]);
+  cudaFree(pk->scratch);
+  pk->msm.release();
+  cudaFree(pk->results);
+  if (pk->results_host) cudaFreeHost(pk->results_host);
+  delete pk;
+}
+
+struct Timing {
+  cudaEvent_t ev[6];
+  float ms[6] = {0, 0, 0, 0, 0, 0};
+  bool init = false;
+};
+static Timing g_timing;  // one key in flight per process
+
+static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
+                    int shard, int nshards, ProvingKey** out) {
+  if (!ctx || !params || !circ || !out || nshards < 1 || shard < 0 || shard >= nshards) {
+    set_error("fb_pk_load: bad argument");
+    return FB_ERR_ARG;
+  }
+  FB_CUDA(cudaSetDevice(ctx->device));
+  ParamsView v;
+  int rc = parse_params(params, len, v);
+  if (rc) return rc;
+  if (v.n_ic != circ->n_in || v.n_l != circ->n_aux) {
+    set_error("Parameters are for n_in=%u n_aux=%u but the circuit has n_in=%u n_aux=%u", v.n_ic,
+              v.n_l, circ->n_in, circ->n_aux);
+    return FB_ERR_ARG;
+  }
+  if (v.n_b1 != v.n_b2) { set_error("b_g1 and b_g2 lengths differ"); return FB_ERR_FORMAT; }
+  ProvingKey* pk = new ProvingKey();
+  pk->ctx = ctx;
+  pk->n_in = circ->n_in;
+  pk->n_aux = circ->n_aux;
+  pk->shard = shard;
+  pk->nshards = nshards;
+  const HostCsr& csr = circ->csr;
+  pk->n_rows = csr.n_gates + pk->n_in;
+  // domain (bellman EvaluationDomain::from_coeffs)
+  uint64_t m = 1;
+  int k = 0;
+  while (m < pk->n_rows) {
+    m *= 2;
+    k++;
+    if (k >= 28) { delete pk; set_error("PolynomialDegreeTooLarge"); return FB_ERR_DOMAIN; }
+  }
+  if (k == 0) { m = 2; k = 1; }  // degenerate single-row circuit: pad to 2
+  pk->k = k;
+  pk->m = m;
+  if (v.n_h + 1 < m) {
+    delete pk;
+    set_error("h query has %u points, need %llu", v.n_h, (unsigned long long)(m - 1));
+    return FB_ERR_FORMAT;
+  }
+  cudaStream_t st = ctx->stream;
+#define PK_TRY(x) do { int _r = (x); if (_r) { pk_release(pk); return _r; } } while (0)
+#define PK_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); pk_release(pk); return FB_ERR_CUDA; } } while (0)
+  // vk points on host
+  if (host_decode_g1(v.alpha_g1, pk->alpha_g1) || host_decode_g1(v.beta_g1, pk->beta_g1) ||
+      host_decode_g1(v.delta_g1, pk->delta_g1) || host_decode_g2(v.beta_g2, pk->beta_g2) ||
+      host_decode_g2(v.delta_g2, pk->delta_g2)) {
+    pk_release(pk);
+    set_error("invalid verifying-key point");
+    return FB_ERR_FORMAT;
+  }
+  // structural density (bellman DensityTracker: a variable counts when it appears)
+  std::vector<uint8_t> a_d(pk->n_in + pk->n_aux, 0), b_d(pk->n_in + pk->n_aux, 0);
+  for (uint32_t c : csr.col[0]) a_d[c] = 1;
+  for (uint32_t c : csr.col[1]) b_d[c] = 1;
+  std::vector<uint32_t> a_map, b_map;
+  for (uint32_t i = 0; i < pk->n_in; i++) a_map.push_back(i);  // inputs: full density
+  for (uint32_t i = 0; i < pk->n_aux; i++) if (a_d[pk->n_in + i]) a_map.push_back(pk->n_in + i);
+  for (uint32_t i = 0; i < pk->n_in + pk->n_aux; i++) if (b_d[i]) b_map.push_back(i);
+  if (a_map.size() != v.n_a || b_map.size() != v.n_b1) {
+    set_error("query/density mismatch: a has %u points for %zu dense variables, b has %u for %zu",
+              v.n_a, a_map.size(), v.n_b1, b_map.size());
+    pk_release(pk);
+    return FB_ERR_DENSITY;
+  }
+  auto slice = [&](uint64_t n, uint64_t& lo, uint64_t& cnt) {
+    lo = n * shard / nshards;
+    cnt = n * (shard + 1) / nshards - lo;
+  };
+  uint64_t lo, cnt;
+  // h: decode all to a temporary, gather this shard's bit-reversed positions
+  {
+    const uint64_t nh = m - 1;
+    G1Affine* tmp = nullptr;
+    PK_CUDA(cudaMalloc(&tmp, m * sizeof(G1Affine)));
+    PK_CUDA(cudaMemsetAsync(tmp, 0, m * sizeof(G1Affine), st));
+    rc = decode_g1_be(v.h, nh, tmp, checked, st);
+    if (rc) { cudaFree(tmp); pk_release(pk); return rc; }
+    slice(nh, lo, cnt);
+    pk->len_h = (uint32_t)cnt;
+    PK_CUDA(cudaMalloc(&pk->h, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+    if (cnt) k_gather_bitrev<<<(unsigned)std::min<uint64_t>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(
+        pk->h, tmp, k, (uint32_t)lo, (uint32_t)cnt);
+    PK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  slice(v.n_l, lo, cnt);
+  PK_CUDA(cudaMalloc(&pk->l, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_TRY(decode_g1_be(v.l + lo * 64, cnt, pk->l, checked, st));
+  slice(v.n_a, lo, cnt);
+  pk->len_a = (uint32_t)cnt;
+  PK_CUDA(cudaMalloc(&pk->a, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_TRY(decode_g1_be(v.a + lo * 64, cnt, pk->a, checked, st));
+  PK_CUDA(cudaMalloc(&pk->a_map, std::max<uint64_t>(cnt, 1) * 4));
+  PK_CUDA(cudaMemcpy(pk->a_map, a_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice));
+  slice(v.n_b1, lo, cnt);
+  pk->len_b = (uint32_t)cnt;
+  PK_CUDA(cudaMalloc(&pk->b1, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_TRY(decode_g1_be(v.b1 + lo * 64, cnt, pk->b1, checked, st));
+  PK_CUDA(cudaMalloc(&pk->b2, std::max<uint64_t>(cnt, 1) * sizeof(G2Affine)));
+  PK_TRY(decode_g2_be(v.b2 + lo * 128, cnt, pk->b2, checked, st));
+  PK_CUDA(cudaMalloc(&pk->b_map, std::max<uint64_t>(cnt, 1) * 4));
+  PK_CUDA(cudaMemcpy(pk->b_map, b_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice));
+  // CSR + domain + workspaces
+  PK_TRY(upload_csr(csr, pk->csr, st));
+  if (pk->dom.init(k, st) != 0) {
+    set_error("NTT domain init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    pk_release(pk);
+    return FB_ERR_CUDA;
+  }
+  PK_CUDA(cudaMalloc(&pk->w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr)));
+  for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->ev[i], m * sizeof(Fr)));
+  PK_CUDA(cudaMalloc(&pk->scratch, m * sizeof(Fr)));
+  uint64_t l_lo, l_cnt;
+  slice(v.n_l, l_lo, l_cnt);
+  pk->plan_h = MsmPlan::make(pk->len_h);
+  pk->plan_l = MsmPlan::make((uint32_t)l_cnt);
+  pk->plan_a = MsmPlan::make(pk->len_a);
+  pk->plan_b = MsmPlan::make(pk->len_b);
+  uint64_t maxn = std::max<uint64_t>(std::max<uint64_t>(pk->len_h, l_cnt),
+                                     std::max<uint64_t>(pk->len_a, pk->len_b));
+  if (pk->msm.alloc(std::max<uint64_t>(maxn, 1), true) != 0) {
+    set_error("MSM scratch allocation failed");
+    pk_release(pk);
+    return FB_ERR_CUDA;
+  }
+  PK_CUDA(cudaMalloc(&pk->results, 5 * sizeof(G2XYZZ)));
+  PK_CUDA(cudaMallocHost(&pk->results_host, 5 * sizeof(G2XYZZ)));
+  PK_CUDA(cudaStreamSynchronize(st));
+  *out = pk;
+  return FB_OK;
+#undef PK_TRY
+#undef PK_CUDA
+}
+
+// ------------------------------------------------------------- assembly ---
+static void fr_canonical(const uint64_t x[4], uint32_t out[8]) {
+  Fr t;
+  memcpy(t.v, x, 32);
+  t = from_mont(t);
+  memcpy(out, t.v, 32);
+}
+
+// SURVEY.md App. C.5:  A = alpha + r*delta + sum_a ;  B = beta2 + s*delta2 + sum_b2 ;
+// C = rs*delta + s*alpha + r*beta1 + s*sum_a + r*sum_b1 + sum_h + sum_l
+static int assemble(const ProvingKey* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
+                    const G1XYZZ& B1, const G2XYZZ& B2, const uint64_t r[4], const uint64_t s[4],
+                    uint8_t proof_raw[256]) {
+  if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) {
+    set_error("UnexpectedIdentity: delta is the point at infinity");
+    return FB_ERR_IDENTITY;
+  }
+  uint32_t rc[8], sc[8], rsc[8];
+  fr_canonical(r, rc);
+  fr_canonical(s, sc);
+  Fr rm, sm;
+  memcpy(rm.v, r, 32);
+  memcpy(sm.v, s, 32);
+  Fr rs = from_mont(mul(rm, sm));
+  memcpy(rsc, rs.v, 32);
+  G1XYZZ d1 = G1XYZZ::from_affine(pk->delta_g1), al = G1XYZZ::from_affine(pk->alpha_g1),
+         be1 = G1XYZZ::from_affine(pk->beta_g1);
+  G2XYZZ d2 = G2XYZZ::from_affine(pk->delta_g2);
+  G1XYZZ g_a = add_cold(add_mixed_cold(scalar_mul(d1, rc), pk->alpha_g1), A);
+  G2XYZZ g_b = add_cold(add_mixed_cold(scalar_mul(d2, sc), pk->beta_g2), B2);
+  G1XYZZ g_c = scalar_mul(d1, rsc);
+  g_c = add_cold(g_c, scalar_mul(al, sc));
+  g_c = add_cold(g_c, scalar_mul(be1, rc));
+  g_c = add_cold(g_c, scalar_mul(A, sc));
+  g_c = add_cold(g_c, scalar_mul(B1, rc));
+  g_c = add_cold(g_c, H);
+  g_c = add_cold(g_c, L);
+  G1Affine pa = to_affine(g_a), pc = to_affine(g_c);
+  G2Affine pb = to_affine(g_b);
+  memcpy(proof_raw, &pa, 64);
+  memcpy(proof_raw + 64, &pb, 128);
+  memcpy(proof_raw + 192, &pc, 64);
+  return FB_OK;
+}
+
+// device part: w already in pk->w.  Leaves five XYZZ sums in pk->results_host.
+static int prove_device_part(ProvingKey* pk, uint64_t* h_out) {
+  cudaStream_t st = pk->ctx->stream;
+  Timing& T = g_timing;
+  if (!T.init) {
+    for (auto& e : T.ev) cudaEventCreate(&e);
+    T.init = true;
+  }
+  const uint64_t m = pk->m;
+  cudaEventRecord(T.ev[1], st);
+  int rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
+  if (rc) return rc;
+  cudaEventRecord(T.ev[2], st);
+  for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(pk->ev[i], st);
+  pk->dom.pointwise_then_icoset_fft(pk->ev[0], pk->ev[1], pk->ev[2], st);
+  cudaEventRecord(T.ev[3], st);
+  if (h_out) {
+    pk->dom.bitrev(pk->scratch, pk->ev[0], st);
+    FB_CUDA(cudaMemcpyAsync(h_out, pk->scratch, (m - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  }
+  G2XYZZ* res = reinterpret_cast<G2XYZZ*>(pk->results);
+  FB_CUDA(cudaMemsetAsync(res, 0, 5 * sizeof(G2XYZZ), st));
+  const uint64_t nh = m - 1;
+  const uint64_t h_lo = nh * pk->shard / pk->nshards;
+  const uint64_t l_lo = (uint64_t)pk->n_aux * pk->shard / pk->nshards;
+  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm, (G1XYZZ*)(res + 0), false, st);
+  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm, (G1XYZZ*)(res + 1), false, st);
+  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm, (G1XYZZ*)(res + 2), false, st);
+  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm, (G1XYZZ*)(res + 3), false, st);
+  if (!rc) rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm, res + 4, true, st);
+  if (rc) { set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
+  cudaEventRecord(T.ev[4], st);
+  FB_CUDA(cudaMemcpyAsync(pk->results_host, res, 5 * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
+  return FB_OK;
+}
+
+static void collect_timings(double host_ms, double total_ms) {
+  Timing& T = g_timing;
+  cudaEventElapsedTime(&T.ms[0], T.ev[0], T.ev[1]);
+  cudaEventElapsedTime(&T.ms[1], T.ev[1], T.ev[2]);
+  cudaEventElapsedTime(&T.ms[2], T.ev[2], T.ev[3]);
+  cudaEventElapsedTime(&T.ms[3], T.ev[3], T.ev[4]);
+  T.ms[4] = (float)host_ms;
+  T.ms[5] = (float)total_ms;
+}
+
+static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t n_in,
+                      const uint64_t* aux, uint32_t n_aux, const void* dev_w, const uint64_t* r,
+                      const uint64_t* s, uint8_t* proof_raw, uint8_t* partial, uint64_t* h_out) {
+  if (!ctx || !pk) { set_error("fb_prove: null handle"); return FB_ERR_ARG; }
+  if (!dev_w && (n_in != pk->n_in || n_aux != pk->n_aux)) {
+    set_error("witness has n_in=%u n_aux=%u, key expects %u / %u", n_in, n_aux, pk->n_in, pk->n_aux);
+    return FB_ERR_ARG;
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  FB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!g_timing.init) {
+    for (auto& e : g_timing.ev) cudaEventCreate(&e);
+    g_timing.init = true;
+  }
+  cudaEventRecord(g_timing.ev[0], st);
+  if (dev_w) {
+    FB_CUDA(cudaMemcpyAsync(pk->w, dev_w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr),
+                            cudaMemcpyDeviceToDevice, st));
+  } else {
+    FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  }
+  int rc = prove_device_part(pk, h_out);
+  if (rc) return rc;
+  auto t1 = std::chrono::steady_clock::now();
+  const G2XYZZ* res = reinterpret_cast<const G2XYZZ*>(pk->results_host);
+  G1XYZZ H = *(const G1XYZZ*)(res + 0), L = *(const G1XYZZ*)(res + 1), A = *(const G1XYZZ*)(res + 2),
+         B1 = *(const G1XYZZ*)(res + 3);
+  G2XYZZ B2 = res[4];
+  if (partial) {
+    memset(partial, 0, 640);
+    G1Affine p;
+    p = to_affine(H); memcpy(partial + 0, &p, 64);
+    p = to_affine(L); memcpy(partial + 128, &p, 64);
+    p = to_affine(A); memcpy(partial + 256, &p, 64);
+    p = to_affine(B1); memcpy(partial + 384, &p, 64);
+    G2Affine q = to_affine(B2);
+    memcpy(partial + 512, &q, 128);
+    rc = FB_OK;
+  } else {
+    rc = assemble(pk, H, L, A, B1, B2, r, s, proof_raw);
+  }
+  auto t2 = std::chrono::steady_clock::now();
+  collect_timings(std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                  std::chrono::duration<double, std::milli>(t2 - t0).count());
+  return rc;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+const char* fb_last_error(void) { return fb::last_error_cstr(); }
+
+int fb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int fb_init(const int* devices, int ndev, fb_ctx** out) {
+  if (!out || ndev != 1) {
+    set_error("fb_init: exactly one device per context (one process per GPU)");
+    return FB_ERR_ARG;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); this backend has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return FB_ERR_CUDA;
+  }
+  int dev = devices ? devices[0] : 0;
+  if (dev < 0 || dev >= n) { set_error("device %d out of range (have %d)", dev, n); return FB_ERR_ARG; }
+  FB_CUDA(cudaSetDevice(dev));
+  Ctx* c = new Ctx();
+  c->device = dev;
+  FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  *out = reinterpret_cast<fb_ctx*>(c);
+  return FB_OK;
+}
+
+void fb_shutdown(fb_ctx* ctx) {
+  Ctx* c = reinterpret_cast<Ctx*>(ctx);
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void fb_free(void* p) { free(p); }
+
+int fb_circuit_from_raw_gates(const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
+                              uint32_t n_aux, fb_circuit** out) {
+  if (!out || (!gates && len)) { set_error("fb_circuit_from_raw_gates: bad argument"); return FB_ERR_ARG; }
+  Circuit* c = new Circuit();
+  c->n_in = n_in;
+  c->n_aux = n_aux;
+  int rc = parse_gates_to_csr(gates, len, n_in, n_aux, c->csr);
+  if (rc) { delete c; return rc; }
+  if (c->csr.n_gates != num_gates) {
+    set_error("gate stream holds %u gates, Parameters announce %u", c->csr.n_gates, num_gates);
+    delete c;
+    return FB_ERR_FORMAT;
+  }
+  *out = reinterpret_cast<fb_circuit*>(c);
+  return FB_OK;
+}
+
+int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_gates, uint32_t n_in,
+                          uint32_t n_aux, fb_circuit** out) {
+  std::vector<uint8_t> raw;
+  int rc = brotli_decode(gates_brotli, len, raw);
+  if (rc) return rc;
+  return fb_circuit_from_raw_gates(raw.data(), raw.size(), num_gates, n_in, n_aux, out);
+}
+
+void fb_circuit_free(fb_circuit* c) { delete reinterpret_cast<Circuit*>(c); }
+
+int fb_circuit_shape(const fb_circuit* c_, uint32_t* n_in, uint32_t* n_aux, uint32_t* n_gates,
+                     uint64_t* nnz) {
+  const Circuit* c = reinterpret_cast<const Circuit*>(c_);
+  if (!c) return FB_ERR_ARG;
+  if (n_in) *n_in = c->n_in;
+  if (n_aux) *n_aux = c->n_aux;
+  if (n_gates) *n_gates = c->csr.n_gates;
+  if (nnz) *nnz = c->csr.col[0].size() + c->csr.col[1].size() + c->csr.col[2].size();
+  return FB_OK;
+}
+
+int fb_pk_load_shard(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
+                     const fb_circuit* circuit, int checked, int shard, int nshards, fb_pk** out) {
+  return load_key(reinterpret_cast<Ctx*>(ctx), bellman_params, len,
+                  reinterpret_cast<const Circuit*>(circuit), checked, shard, nshards,
+                  reinterpret_cast<ProvingKey**>(out));
+}
+
+int fb_pk_load_circuit(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
+                       const fb_circuit* circuit, int checked, fb_pk** out) {
+  return fb_pk_load_shard(ctx, bellman_params, len, circuit, checked, 0, 1, out);
+}
+
+int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uint8_t* gates_brotli,
+               size_t glen, uint32_t num_gates, int checked, fb_pk** out) {
+  ParamsView v;
+  int rc = parse_params(bellman_params, len, v);
+  if (rc) return rc;
+  fb_circuit* c = nullptr;
+  rc = fb_circuit_from_gates(gates_brotli, glen, num_gates, v.n_ic, v.n_l, &c);
+  if (rc) return rc;
+  rc = fb_pk_load_circuit(ctx, bellman_params, len, c, checked, out);
+  fb_circuit_free(c);
+  return rc;
+}
+
+void fb_pk_free(fb_pk* pk) {
+  ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
+  if (p && p->ctx) cudaSetDevice(p->ctx->device);
+  pk_release(p);
+}
+
+int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
+  const ProvingKey* pk = reinterpret_cast<const ProvingKey*>(pk_);
+  if (!pk || !info) return FB_ERR_ARG;
+  info->n_in = pk->n_in;
+  info->n_aux = pk->n_aux;
+  info->n_gates = pk->csr.n_gates;
+  info->log_m = pk->k;
+  info->len_h = pk->len_h;
+  info->len_l = pk->plan_l.n;
+  info->len_a = pk->len_a;
+  info->len_b = pk->len_b;
+  info->nnz = pk->csr.nnz[0] + pk->csr.nnz[1] + pk->csr.nnz[2];
+  uint64_t b = (uint64_t)pk->len_h * 64 + (uint64_t)pk->plan_l.n * 64 + (uint64_t)pk->len_a * 68 +
+               (uint64_t)pk->len_b * (64 + 128 + 4) + info->nnz * 8 + 5 * pk->m * 32 +
+               3 * (pk->m - 1) * 32 + (uint64_t)(pk->n_in + pk->n_aux) * 32;
+  info->hbm_bytes = b;
+  return FB_OK;
+}
+
+int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
+             uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
+             uint64_t* h_out) {
+  if (!inputs || (!aux && n_aux) || !r || !s || !proof_raw) { set_error("fb_prove: null buffer"); return FB_ERR_ARG; }
+  ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
+  if (p && p->nshards != 1) { set_error("fb_prove on a sharded key: use fb_prove_partial"); return FB_ERR_ARG; }
+  return prove_impl(reinterpret_cast<Ctx*>(ctx), p, inputs, n_in, aux, n_aux, nullptr, r, s,
+                    proof_raw, nullptr, h_out);
+}
+
+int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
+                    const uint64_t s[4], uint8_t proof_raw[256]) {
+  if (!dev_w || !r || !s || !proof_raw) { set_error("fb_prove_device: null buffer"); return FB_ERR_ARG; }
+  ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
+  if (p && p->nshards != 1) { set_error("fb_prove_device on a sharded key"); return FB_ERR_ARG; }
+  return prove_impl(reinterpret_cast<Ctx*>(ctx), p, nullptr, 0, nullptr, 0, dev_w, r, s, proof_raw,
+                    nullptr, nullptr);
+}
+
+int fb_prove_partial(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in,
+                     const uint64_t* aux, uint32_t n_aux, uint8_t partial[640]) {
+  if (!inputs || (!aux && n_aux) || !partial) { set_error("fb_prove_partial: null buffer"); return FB_ERR_ARG; }
+  return prove_impl(reinterpret_cast<Ctx*>(ctx), reinterpret_cast<ProvingKey*>(pk), inputs, n_in, aux,
+                    n_aux, nullptr, nullptr, nullptr, nullptr, partial, nullptr);
+}
+
+int fb_prove_finish(const fb_pk* pk_, const uint8_t* partials, int nparts, const uint64_t r[4],
+                    const uint64_t s[4], uint8_t proof_raw[256]) {
+  const ProvingKey* pk = reinterpret_cast<const ProvingKey*>(pk_);
+  if (!pk || !partials || nparts < 1 || !r || !s || !proof_raw) { set_error("fb_prove_finish: bad argument"); return FB_ERR_ARG; }
+  G1XYZZ sum[4] = {G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf()};
+  G2XYZZ sum2 = G2XYZZ::inf();
+  for (int i = 0; i < nparts; i++) {
+    const uint8_t* p = partials + (size_t)i * 640;
+    for (int j = 0; j < 4; j++) {
+      G1Affine a;
+      memcpy(&a, p + 128 * j, 64);
+      sum[j] = add_mixed_cold(sum[j], a);
+    }
+    G2Affine q;
+    memcpy(&q, p + 512, 128);
+    sum2 = add_mixed_cold(sum2, q);
+  }
+  return assemble(pk, sum[0], sum[1], sum[2], sum[3], sum2, r, s, proof_raw);
+}
+
+int fb_prove_timings(const fb_pk* pk, float ms[6]) {
+  if (!pk || !ms) return FB_ERR_ARG;
+  for (int i = 0; i < 6; i++) ms[i] = g_timing.ms[i];
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Internal structures shared by the translation units of libfawkes_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/fawkes_b200.h"
+#include "ec.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace fb {
+
+void set_error(const char* fmt, ...);
+#define FB_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t _e = (call);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      fb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+      return FB_ERR_CUDA;                                                      \
+    }                                                                              \
+  } while (0)
+
+// R1CS in CSR form over the concatenated variable vector w = [inputs | aux].
+struct HostCsr {
+  std::vector<uint32_t> rowptr[3];  // n_gates + 1 each
+  std::vector<uint32_t> col[3];
+  std::vector<uint32_t> cidx[3];    // 0 -> ONE, 1 -> -ONE, k>=2 -> coef[k-2]
+  std::vector<Fr> coef;             // Montgomery
+  uint32_t n_gates = 0;
+};
+
+struct DevCsr {
+  uint32_t* rowptr[3] = {nullptr, nullptr, nullptr};
+  uint32_t* col[3] = {nullptr, nullptr, nullptr};
+  uint32_t* cidx[3] = {nullptr, nullptr, nullptr};
+  Fr* coef = nullptr;
+  uint32_t n_gates = 0;
+  uint64_t nnz[3] = {0, 0, 0};
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+};
+
+struct ProvingKey {
+  Ctx* ctx = nullptr;
+  uint32_t n_in = 0, n_aux = 0, n_rows = 0;
+  int k = 0;           // log2 domain size
+  uint64_t m = 0;
+  // verifying-key points needed by the prover (host, Montgomery affine)
+  G1Affine alpha_g1, beta_g1, delta_g1;
+  G2Affine beta_g2, delta_g2;
+  // base arrays in HBM
+  G1Affine* h = nullptr;   // m-1 points, bit-reversed order
+  G1Affine* l = nullptr;   // n_aux
+  G1Affine* a = nullptr;   // len_a
+  G1Affine* b1 = nullptr;  // len_b
+  G2Affine* b2 = nullptr;  // len_b
+  uint32_t len_h = 0, len_a = 0, len_b = 0;
+  uint32_t* a_map = nullptr;  // into w
+  uint32_t* b_map = nullptr;
+  DevCsr csr;
+  NttDomain dom;
+  // per-prove workspace
+  Fr* w = nullptr;         // n_in + n_aux
+  Fr* ev[3] = {nullptr, nullptr, nullptr};  // m each
+  Fr* scratch = nullptr;   // m (h_out permutation)
+  MsmScratch msm;
+  MsmPlan plan_h, plan_l, plan_a, plan_b;
+  void* results = nullptr;       // 5 x G2XYZZ slots on device
+  void* results_host = nullptr;  // pinned
+  // base-index shard handled by this key (multi-GPU): fractions [shard, shard+1)/nshards
+  int shard = 0, nshards = 1;
+};
+
+struct Circuit {
+  HostCsr csr;
+  uint32_t n_in = 0, n_aux = 0;
+  std::vector<Fr> inputs, aux;  // synthetic circuits only (Montgomery)
+};
+
+struct ParamsView {  // offsets into bellman Parameters bytes
+  const uint8_t *alpha_g1, *beta_g1, *beta_g2, *gamma_g2, *delta_g1, *delta_g2;
+  const uint8_t *ic, *h, *l, *a, *b1, *b2;
+  uint32_t n_ic, n_h, n_l, n_a, n_b1, n_b2;
+};
+int parse_params(const uint8_t* b, size_t len, ParamsView& v);  // api.cu
+
+// pk.cu
+int parse_gates_to_csr(const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out);
+int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out);
+int upload_csr(const HostCsr& h, DevCsr& d, cudaStream_t st);
+void free_csr(DevCsr& d);
+int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, bool checked, cudaStream_t st);
+int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, bool checked, cudaStream_t st);
+int host_decode_g1(const uint8_t* be, G1Affine& out);
+int host_decode_g2(const uint8_t* be, G2Affine& out);
+void host_encode_g1(const G1Affine& p, uint8_t* be);
+void host_encode_g2(const G2Affine& p, uint8_t* be);
+
+// prove.cu
+int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,
+              cudaStream_t st);
+
+}  // namespace fb

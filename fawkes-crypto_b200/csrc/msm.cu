@@ -1,0 +1,324 @@
+// See msm.cuh for the design and the reference interface this replaces.
+#include "msm.cuh"
+
+#include <cstdlib>
+
+namespace fb {
+
+// ------------------------------------------------------------------ plan ---
+MsmPlan MsmPlan::make(uint32_t n) {
+  MsmPlan p;
+  p.n = n;
+  int lg = 0;
+  while ((2u << lg) <= n && lg < 31) lg++;
+  int c = lg - 6;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  if (const char* e = getenv("FB_MSM_C")) {
+    int v = atoi(e);
+    if (v >= 2 && v <= 24) c = v;
+  }
+  p.c = c;
+  p.W = (255 + c - 1) / c;
+  p.B = 1u << (c - 1);
+  p.seg_log = c - 1 < 5 ? c - 1 : 5;
+  return p;
+}
+
+int MsmScratch::alloc(uint64_t max_n, bool need_g2) {
+  // worst case over all plans up to max_n: entries = n * W, buckets = W * B
+  uint64_t ent = 0, bk = 0;
+  for (uint64_t n = 1; n <= max_n; n = n * 2) {
+    uint64_t nn = n * 2 - 1 < max_n ? n * 2 - 1 : max_n;
+    MsmPlan p = MsmPlan::make((uint32_t)nn);
+    ent = std::max<uint64_t>(ent, (uint64_t)nn * p.W);
+    bk = std::max<uint64_t>(bk, p.nbuckets());
+  }
+  MsmPlan p = MsmPlan::make((uint32_t)max_n);
+  ent = std::max<uint64_t>(ent, (uint64_t)max_n * p.W);
+  bk = std::max<uint64_t>(bk, p.nbuckets());
+  cap_entries = ent;
+  cap_buckets = bk;
+  size_t psz = need_g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
+  if (cudaMalloc(&hist, (bk + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&offsets, (bk + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&cursor, (bk + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&blocksums, ((bk + 1023) / 1024 + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&sorted, std::max<uint64_t>(ent, 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&buckets, bk * psz) != cudaSuccess) return -1;
+  if (cudaMalloc(&segR, bk * psz) != cudaSuccess) return -1;  // nsegs <= nbuckets
+  if (cudaMalloc(&segS, bk * psz) != cudaSuccess) return -1;
+  if (cudaMalloc(&winsum, 256 * psz) != cudaSuccess) return -1;
+  return 0;
+}
+
+void MsmScratch::release() {
+  cudaFree(hist); cudaFree(offsets); cudaFree(cursor); cudaFree(blocksums); cudaFree(sorted);
+  cudaFree(buckets); cudaFree(segR); cudaFree(segS); cudaFree(winsum);
+  hist = offsets = cursor = blocksums = sorted = nullptr;
+  buckets = segR = segS = winsum = nullptr;
+}
+
+// ---------------------------------------------------------------- digits ---
+__device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int c) {
+  const int limb = pos >> 5, sh = pos & 31;
+  if (limb >= 8) return 0;
+  uint64_t v = s[limb];
+  if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+  return (uint32_t)(v >> sh) & ((1u << c) - 1);
+}
+
+// SCATTER=false: histogram.  SCATTER=true: place entries using cursor (pre-loaded with offsets).
+template <bool SCATTER>
+__global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restrict__ map,
+                         uint32_t n, int c, int W, uint32_t B, uint32_t* __restrict__ counter,
+                         uint32_t* __restrict__ sorted) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    Fr s = from_mont(scalars[map ? map[i] : i]);
+    uint32_t carry = 0;
+    for (int w = 0; w < W; w++) {
+      uint32_t v = window_bits(s.v, w * c, c) + carry;
+      uint32_t neg = 0, mag = v;
+      if (v > B) {  // v in (2^(c-1), 2^c] -> negative digit v - 2^c, carry 1
+        mag = (1u << c) - v;
+        neg = 1;
+        carry = 1;
+      } else {
+        carry = 0;
+      }
+      if (mag != 0) {
+        uint32_t bucket = (uint32_t)w * B + mag - 1;
+        uint32_t pos = atomicAdd(&counter[bucket], 1u);
+        if (SCATTER) sorted[pos] = i | (neg << 31);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ scan ---
+__global__ void k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                             uint32_t* __restrict__ blocksums, uint32_t n) {
+  __shared__ uint32_t wsum[32];
+  const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+  uint32_t v = i < n ? in[i] : 0;
+  uint32_t x = v;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+    if (lane >= d) x += y;
+  }
+  if (lane == 31) wsum[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += y;
+    }
+    wsum[lane] = w;
+  }
+  __syncthreads();
+  uint32_t incl = x + (wid ? wsum[wid - 1] : 0);
+  if (i < n) out[i] = incl - v;  // exclusive within block
+  if (threadIdx.x == 1023) blocksums[blockIdx.x] = incl;
+}
+__global__ void k_scan_sums(uint32_t* blocksums, uint32_t nb) {  // single thread block, serial over chunks
+  __shared__ uint32_t carry_s;
+  __shared__ uint32_t wsum[32];
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nb; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nb ? blocksums[i] : 0, x = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    uint32_t incl = x + (wid ? wsum[wid - 1] : 0) + carry_s;
+    if (i < nb) blocksums[i] = incl - v;  // exclusive
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = incl;
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cursor,
+                           const uint32_t* __restrict__ blocksums, uint32_t n) {
+  const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+  if (i < n) {
+    uint32_t v = out[i] + blocksums[blockIdx.x];
+    out[i] = v;
+    cursor[i] = v;
+  }
+}
+
+// ------------------------------------------------------------ accumulate ---
+template <class F>
+__global__ void __launch_bounds__(128)
+k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+             const uint32_t* __restrict__ offsets, uint32_t nb, XYZZ<F>* __restrict__ buckets) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const uint32_t start = offsets[b], end = offsets[b + 1];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (start < end) {
+    uint32_t e = sorted[start];
+    Affine<F> nxt = bases[e & 0x7fffffffu];
+    for (uint32_t p = start; p < end; p++) {
+      Affine<F> cur = nxt;
+      const uint32_t sign = e >> 31;
+      if (p + 1 < end) {
+        e = sorted[p + 1];
+        nxt = bases[e & 0x7fffffffu];
+      }
+      if (sign) cur.y = neg(cur.y);
+      acc = add_mixed(acc, cur);
+    }
+  }
+  buckets[b] = acc;
+}
+
+// ---------------------------------------------------------------- reduce ---
+// per segment of K = 2^seg_log buckets:  R = sum (t+1) * B_t,  S = sum B_t
+template <class F>
+__global__ void __launch_bounds__(128)
+k_reduce_seg(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, int seg_log,
+             XYZZ<F>* __restrict__ segR, XYZZ<F>* __restrict__ segS) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsegs) return;
+  const uint32_t K = 1u << seg_log;
+  const XYZZ<F>* bk = buckets + ((uint64_t)s << seg_log);
+  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+  for (int t = (int)K - 1; t >= 0; t--) {
+    run = add_cold(run, bk[t]);
+    tot = add_cold(tot, run);
+  }
+  segR[s] = tot;
+  segS[s] = run;
+}
+
+// one warp per window: winsum = sum_s R_s + K * sum_s s * S_s
+template <class F>
+__global__ void __launch_bounds__(32)
+k_reduce_win(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ segS, uint32_t segs,
+             int seg_log, XYZZ<F>* __restrict__ winsum) {
+  __shared__ XYZZ<F> shR[32], shW[32], shS[32];
+  const uint32_t w = blockIdx.x, lane = threadIdx.x;
+  const XYZZ<F>* R = segR + (uint64_t)w * segs;
+  const XYZZ<F>* S = segS + (uint64_t)w * segs;
+  // lane handles segments [lo, hi); chunk = ceil(segs / 32)
+  const uint32_t chunk = (segs + 31) / 32;
+  const uint32_t lo = lane * chunk, hi = min(segs, lo + chunk);
+  XYZZ<F> sumR = XYZZ<F>::inf(), run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+  for (int s = (int)hi - 1; s >= (int)lo; s--) {
+    sumR = add_cold(sumR, R[s]);
+    run = add_cold(run, S[s]);
+    tot = add_cold(tot, run);  // sum (s - lo + 1) * S_s
+  }
+  shR[lane] = sumR;  // sum of R
+  shW[lane] = tot;   // local weighted (weights 1..)
+  shS[lane] = run;   // plain sum of S
+  __syncwarp();
+  if (lane == 0) {
+    // sum_s s*S_s = sum_lanes [ (W_lane - S_lane) + lo_lane * S_lane ],  lo_lane = lane*chunk
+    XYZZ<F> accR = XYZZ<F>::inf(), accW = XYZZ<F>::inf(), accS = XYZZ<F>::inf();
+    XYZZ<F> run2 = XYZZ<F>::inf(), tot2 = XYZZ<F>::inf();  // sum lane * S_lane via running sum
+    for (int l = 31; l >= 0; l--) {
+      accR = add_cold(accR, shR[l]);
+      accW = add_cold(accW, shW[l]);
+      accS = add_cold(accS, shS[l]);
+      if (l >= 1) {
+        run2 = add_cold(run2, shS[l]);
+        tot2 = add_cold(tot2, run2);
+      }
+    }
+    // chunk * tot2 by double-and-add on the small integer chunk
+    XYZZ<F> ct = XYZZ<F>::inf();
+    for (int bit = 31; bit >= 0; bit--) {
+      ct = dbl_cold(ct);
+      if ((chunk >> bit) & 1) ct = add_cold(ct, tot2);
+    }
+    XYZZ<F> T = add_cold(add_cold(accW, neg(accS)), ct);  // sum_s s * S_s
+    for (int i = 0; i < seg_log; i++) T = dbl_cold(T);
+    winsum[w] = add_cold(accR, T);
+  }
+}
+
+// result = sum_w 2^(c w) * winsum[w]
+template <class F>
+__global__ void __launch_bounds__(64)
+k_combine(const XYZZ<F>* __restrict__ winsum, int W, int c, XYZZ<F>* __restrict__ out) {
+  __shared__ XYZZ<F> sh[64];
+  const int w = threadIdx.x;
+  if (w < W) {
+    XYZZ<F> x = winsum[w];
+    for (int i = 0; i < w * c; i++) x = dbl_cold(x);
+    sh[w] = x;
+  }
+  __syncthreads();
+  if (w == 0) {
+    XYZZ<F> acc = sh[0];
+    for (int i = 1; i < W; i++) acc = add_cold(acc, sh[i]);
+    *out = acc;
+  }
+}
+
+// ----------------------------------------------------------------- driver ---
+template <class F>
+static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* map,
+                   const MsmPlan& p, MsmScratch& s, XYZZ<F>* out, bool reuse_sort,
+                   cudaStream_t st) {
+  const uint32_t nb = p.nbuckets();
+  if (p.W > 64) return -1;
+  if (p.n == 0) {
+    cudaMemsetAsync(out, 0, sizeof(XYZZ<F>), st);
+    return 0;
+  }
+  if ((uint64_t)p.n * p.W > s.cap_entries || nb > s.cap_buckets) return -2;
+  if (!reuse_sort) {
+    cudaMemsetAsync(s.hist, 0, (size_t)(nb + 1) * 4, st);
+    const unsigned dg = (unsigned)std::min<uint64_t>((p.n + 255) / 256, 148 * 16);
+    k_digits<false><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, s.hist, nullptr);
+    const unsigned sb = (nb + 1 + 1023) / 1024;
+    k_scan_block<<<sb, 1024, 0, st>>>(s.hist, s.offsets, s.blocksums, nb + 1);
+    k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb);
+    k_scan_add<<<sb, 1024, 0, st>>>(s.offsets, s.cursor, s.blocksums, nb + 1);
+    k_digits<true><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, s.cursor, s.sorted);
+  }
+  XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(s.buckets);
+  XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
+  XYZZ<F>* segS = reinterpret_cast<XYZZ<F>*>(s.segS);
+  XYZZ<F>* winsum = reinterpret_cast<XYZZ<F>*>(s.winsum);
+  k_accumulate<F><<<(nb + 127) / 128, 128, 0, st>>>(bases, s.sorted, s.offsets, nb, buckets);
+  const uint32_t nsegs = p.nsegs();
+  k_reduce_seg<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
+  k_reduce_win<F><<<p.W, 32, 0, st>>>(segR, segS, p.B >> p.seg_log, p.seg_log, winsum);
+  k_combine<F><<<1, 64, 0, st>>>(winsum, p.W, p.c, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
+           MsmScratch& s, G1XYZZ* out, bool reuse_sort, cudaStream_t st) {
+  return msm_run<Fq>(bases, scalars, map, plan, s, out, reuse_sort, st);
+}
+int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
+           MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st) {
+  return msm_run<Fq2>(bases, scalars, map, plan, s, out, reuse_sort, st);
+}
+
+}  // namespace fb

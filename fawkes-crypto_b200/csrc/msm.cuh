@@ -1,0 +1,62 @@
+// Pippenger bucket multi-scalar multiplication for BN254 G1 / G2 on sm_100a.
+//
+// Replaces bellman_ce's `multiexp` (un-vendored; eight call sites inside
+// create_random_proof, reached from fawkes-crypto/src/backend/bellman_groth16/
+// prover.rs:80).  The result sum_i s_i * P_i is a unique group
+// element, so a different window size / digit encoding / coordinate system than
+// bellman's (c = ln n unsigned windows, Jacobian) gives byte-identical affine output.
+//
+// Pipeline (all on one stream):
+//   1. k_digits_count  canonical scalar (one Montgomery multiply by 1) -> signed
+//                      base-2^c digits d in [-2^(c-1), 2^(c-1)], histogram of
+//                      bucket = window * 2^(c-1) + |d| - 1
+//   2. k_scan_*        exclusive prefix sum of the histogram (bucket offsets)
+//   3. k_scatter       counting-sort placement of (point index | sign << 31)
+//   4. k_accumulate    one thread per bucket, XYZZ mixed adds over its run, next base
+//                      prefetched while the current add executes
+//   5. k_reduce_*      sum_j (j+1) * B_j per window by segmented running sums
+//   6. k_combine       Horner over windows with c doublings between
+// Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "ec.cuh"
+
+namespace fb {
+
+struct MsmPlan {
+  uint32_t n = 0;       // number of (scalar, base) pairs
+  int c = 0;            // window bits
+  int W = 0;            // number of windows, W*c >= 255
+  uint32_t B = 0;       // buckets per window = 2^(c-1)
+  int seg_log = 0;      // buckets per reduce segment = 2^seg_log
+  static MsmPlan make(uint32_t n);
+  uint32_t nbuckets() const { return (uint32_t)W * B; }
+  uint32_t nsegs() const { return nbuckets() >> seg_log; }
+};
+
+// Scratch shared by consecutive MSMs on one stream (sized for the largest plan).
+struct MsmScratch {
+  uint32_t* hist = nullptr;     // [nbuckets + 1]
+  uint32_t* offsets = nullptr;  // [nbuckets + 1]
+  uint32_t* cursor = nullptr;   // [nbuckets]
+  uint32_t* blocksums = nullptr;
+  uint32_t* sorted = nullptr;   // [n * W]
+  void* buckets = nullptr;      // [nbuckets] XYZZ (sized for G2)
+  void* segR = nullptr;         // [nsegs] XYZZ
+  void* segS = nullptr;         // [nsegs] XYZZ
+  void* winsum = nullptr;       // [W] XYZZ
+  size_t cap_entries = 0, cap_buckets = 0;
+  int alloc(uint64_t max_n, bool need_g2);
+  void release();
+};
+
+// scalars: Montgomery Fr, addressed as scalars[map ? map[i] : i]; bases: affine Montgomery.
+// result: one XYZZ point on device (out).  Steps 1-3 are skipped when reuse_sort is set
+// (same scalars as the previous call on this scratch: B_g1 then B_g2).
+int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
+           MsmScratch& s, G1XYZZ* out, bool reuse_sort, cudaStream_t st);
+int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
+           MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st);
+
+}  // namespace fb

@@ -1,0 +1,303 @@
+// Proving-key ingest: bellman Parameters bytes -> HBM-resident Montgomery affine bases,
+// gate blob -> CSR.
+//
+// Follows (reference side of the boundary):
+//   Parameters framing / read           fawkes-crypto/src/backend/bellman_groth16/mod.rs:150-175
+//   gate stream: brotli -> borsh, 37 B per term (32 B canonical LE coeff, u8 tag, u32 LE idx)
+//                                        fawkes-crypto/src/circuit/r1cs/cs.rs:184-223,248-250
+//   Index tag 0 = Input, 1 = Aux         fawkes-crypto/src/circuit/r1cs/lc.rs:144-149
+//   variables: inputs (ONE first) then aux   backend/bellman_groth16/mod.rs:61-102
+// bellman's own point encoding (big-endian uncompressed, 0x40 flag = infinity) is restated
+// from bellman_ce 0.3.5 / pairing_ce 0.18.1, absent from the repo.
+#include <dlfcn.h>
+
+#include <cstring>
+#include <unordered_map>
+
+#include "internal.h"
+
+namespace fb {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+const char* last_error_cstr() { return g_err.c_str(); }
+
+// ---------------------------------------------------------------- brotli ---
+// libbrotlidec.so.1 ships without headers in this image: bind the three symbols we need.
+typedef struct BrotliDecoderStateStruct BrotliDecoderState;
+typedef BrotliDecoderState* (*fn_create)(void*, void*, void*);
+typedef int (*fn_stream)(BrotliDecoderState*, size_t*, const uint8_t**, size_t*, uint8_t**, size_t*);
+typedef void (*fn_destroy)(BrotliDecoderState*);
+
+int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out) {
+  static void* lib = nullptr;
+  static fn_create create;
+  static fn_stream stream;
+  static fn_destroy destroy;
+  if (!lib) {
+    lib = dlopen("libbrotlidec.so.1", RTLD_NOW);
+    if (!lib) {
+      set_error("cannot load libbrotlidec.so.1: %s", dlerror());
+      return FB_ERR_FORMAT;
+    }
+    create = (fn_create)dlsym(lib, "BrotliDecoderCreateInstance");
+    stream = (fn_stream)dlsym(lib, "BrotliDecoderDecompressStream");
+    destroy = (fn_destroy)dlsym(lib, "BrotliDecoderDestroyInstance");
+    if (!create || !stream || !destroy) {
+      set_error("libbrotlidec.so.1 lacks the streaming API");
+      return FB_ERR_FORMAT;
+    }
+  }
+  BrotliDecoderState* st = create(nullptr, nullptr, nullptr);
+  out.clear();
+  out.resize(std::max<size_t>(len * 4, 1 << 16));
+  size_t avail_in = len, produced = 0;
+  const uint8_t* next_in = in;
+  for (;;) {
+    size_t avail_out = out.size() - produced;
+    uint8_t* next_out = out.data() + produced;
+    int r = stream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
+    produced = out.size() - avail_out;
+    if (r == 1) break;                       // BROTLI_DECODER_RESULT_SUCCESS
+    if (r == 3) { out.resize(out.size() * 2); continue; }  // NEEDS_MORE_OUTPUT
+    // error or truncated input: the reference's Decompressor would surface a read
+    // error and GateStreamedIterator stops (cs.rs:215-223); keep what was produced.
+    break;
+  }
+  destroy(st);
+  out.resize(produced);
+  return FB_OK;
+}
+
+// ------------------------------------------------------------- gate parse ---
+struct FrKey {
+  uint64_t w[4];
+  bool operator==(const FrKey& o) const { return !memcmp(w, o.w, 32); }
+};
+struct FrKeyHash {
+  size_t operator()(const FrKey& k) const {
+    uint64_t h = k.w[0] * 0x9E3779B97F4A7C15ull;
+    h ^= (k.w[1] + 0xBF58476D1CE4E5B9ull) * 0x94D049BB133111EBull;
+    h ^= (k.w[2] << 7) ^ (k.w[3] >> 3) ^ (k.w[3] * 0xD6E8FEB86659FD93ull);
+    return (size_t)h;
+  }
+};
+
+int parse_gates_to_csr(const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out) {
+  static const uint32_t kDedupCap = 1u << 20;
+  std::unordered_map<FrKey, uint32_t, FrKeyHash> dict;
+  for (int m = 0; m < 3; m++) {
+    out.rowptr[m].clear();
+    out.rowptr[m].push_back(0);
+    out.col[m].clear();
+    out.cidx[m].clear();
+  }
+  out.coef.clear();
+  Fr minus_one = neg(Fr::one());
+  size_t pos = 0;
+  uint32_t gates = 0;
+  for (;;) {
+    // a gate is only accepted if all three parts parse (cs.rs:215-223)
+    size_t save[3] = {out.col[0].size(), out.col[1].size(), out.col[2].size()};
+    size_t save_coef = out.coef.size();
+    bool ok = true;
+    for (int m = 0; m < 3 && ok; m++) {
+      if (pos + 4 > len) { ok = false; break; }
+      uint32_t cnt;
+      memcpy(&cnt, raw + pos, 4);
+      pos += 4;
+      if ((size_t)cnt * 37 > len - pos) { ok = false; break; }
+      for (uint32_t t = 0; t < cnt; t++) {
+        Fr c;
+        memcpy(c.v, raw + pos, 32);
+        uint8_t tag = raw[pos + 32];
+        uint32_t idx;
+        memcpy(&idx, raw + pos + 33, 4);
+        pos += 37;
+        if (geq_mod<FrCfg>(c.v) || tag > 1) { ok = false; break; }  // "Wrong raw integer" / enum overflow
+        if ((tag == 0 && idx >= n_in) || (tag == 1 && idx >= n_aux)) {
+          set_error("gate %u references %s variable %u out of range", gates, tag ? "aux" : "input", idx);
+          return FB_ERR_FORMAT;
+        }
+        Fr cm = to_mont(c);
+        uint32_t ci;
+        if (cm == Fr::one()) ci = 0;
+        else if (cm == minus_one) ci = 1;
+        else {
+          FrKey key;
+          memcpy(key.w, cm.v, 32);
+          auto it = dict.find(key);
+          if (it != dict.end()) ci = it->second;
+          else {
+            ci = (uint32_t)out.coef.size() + 2;
+            out.coef.push_back(cm);
+            if (dict.size() < kDedupCap) dict.emplace(key, ci);
+          }
+        }
+        out.col[m].push_back(tag == 0 ? idx : n_in + idx);
+        out.cidx[m].push_back(ci);
+      }
+    }
+    if (!ok) {
+      for (int m = 0; m < 3; m++) { out.col[m].resize(save[m]); out.cidx[m].resize(save[m]); }
+      (void)save_coef;  // coefficients appended by a rejected gate stay unused
+      break;
+    }
+    for (int m = 0; m < 3; m++) out.rowptr[m].push_back((uint32_t)out.col[m].size());
+    gates++;
+  }
+  out.n_gates = gates;
+  return FB_OK;
+}
+
+int upload_csr(const HostCsr& h, DevCsr& d, cudaStream_t st) {
+  d.n_gates = h.n_gates;
+  for (int m = 0; m < 3; m++) {
+    d.nnz[m] = h.col[m].size();
+    FB_CUDA(cudaMalloc(&d.rowptr[m], h.rowptr[m].size() * 4));
+    FB_CUDA(cudaMalloc(&d.col[m], std::max<size_t>(h.col[m].size(), 1) * 4));
+    FB_CUDA(cudaMalloc(&d.cidx[m], std::max<size_t>(h.cidx[m].size(), 1) * 4));
+    FB_CUDA(cudaMemcpyAsync(d.rowptr[m], h.rowptr[m].data(), h.rowptr[m].size() * 4, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(d.col[m], h.col[m].data(), h.col[m].size() * 4, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(d.cidx[m], h.cidx[m].data(), h.cidx[m].size() * 4, cudaMemcpyHostToDevice, st));
+  }
+  FB_CUDA(cudaMalloc(&d.coef, std::max<size_t>(h.coef.size(), 1) * sizeof(Fr)));
+  FB_CUDA(cudaMemcpyAsync(d.coef, h.coef.data(), h.coef.size() * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  return FB_OK;
+}
+
+void free_csr(DevCsr& d) {
+  for (int m = 0; m < 3; m++) {
+    cudaFree(d.rowptr[m]); cudaFree(d.col[m]); cudaFree(d.cidx[m]);
+    d.rowptr[m] = d.col[m] = d.cidx[m] = nullptr;
+  }
+  cudaFree(d.coef);
+  d.coef = nullptr;
+}
+
+// ----------------------------------------------------- point (de)coding ---
+// 32 big-endian bytes -> canonical limbs
+FB_HD void be_to_limbs(const uint8_t* be, uint32_t* v) {
+  for (int i = 0; i < 8; i++) {
+    const uint8_t* p = be + 32 - 4 * (i + 1);
+    v[i] = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+  }
+}
+FB_HD void limbs_to_be(const uint32_t* v, uint8_t* be) {
+  for (int i = 0; i < 8; i++) {
+    uint8_t* p = be + 32 - 4 * (i + 1);
+    p[0] = v[i] >> 24; p[1] = v[i] >> 16; p[2] = v[i] >> 8; p[3] = v[i];
+  }
+}
+
+// returns 0 ok, 1 = coordinate >= p, 2 = not on curve, 3 = bad flag
+FB_HD int decode_g1(const uint8_t* be, G1Affine& out, bool checked) {
+  if (be[0] & 0x40) { out = G1Affine::inf(); return 0; }
+  if (be[0] & 0x80) return 3;
+  Fq x, y;
+  be_to_limbs(be, x.v);
+  be_to_limbs(be + 32, y.v);
+  if (geq_mod<FqCfg>(x.v) || geq_mod<FqCfg>(y.v)) return 1;
+  out.x = to_mont(x);
+  out.y = to_mont(y);
+  if (checked && !on_curve(out, g1_b())) return 2;
+  return 0;
+}
+FB_HD int decode_g2(const uint8_t* be, G2Affine& out, bool checked) {
+  if (be[0] & 0x40) { out = G2Affine::inf(); return 0; }
+  if (be[0] & 0x80) return 3;
+  Fq c[4];
+  for (int i = 0; i < 4; i++) {
+    be_to_limbs(be + 32 * i, c[i].v);
+    if (geq_mod<FqCfg>(c[i].v)) return 1;
+    c[i] = to_mont(c[i]);
+  }
+  out.x = {c[1], c[0]};  // bytes are x.c1 | x.c0 | y.c1 | y.c0
+  out.y = {c[3], c[2]};
+  if (checked && !on_curve(out, g2_b())) return 2;
+  return 0;
+}
+
+__global__ void k_decode_g1(const uint8_t* __restrict__ be, uint64_t n, G1Affine* __restrict__ out,
+                            bool checked, int* __restrict__ err) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    G1Affine p;
+    int e = decode_g1(be + i * 64, p, checked);
+    if (e) atomicMax(err, e);
+    else out[i] = p;
+  }
+}
+__global__ void k_decode_g2(const uint8_t* __restrict__ be, uint64_t n, G2Affine* __restrict__ out,
+                            bool checked, int* __restrict__ err) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    G2Affine p;
+    int e = decode_g2(be + i * 128, p, checked);
+    if (e) atomicMax(err, e);
+    else out[i] = p;
+  }
+}
+
+template <class P, int SZ, class K>
+static int decode_points(const uint8_t* host_be, uint64_t n, P* dev_out, bool checked,
+                         cudaStream_t st, K kernel) {
+  if (n == 0) return FB_OK;
+  // stage through a bounded device buffer so a 16 GiB key does not need 16 GiB of staging
+  const uint64_t chunk = std::min<uint64_t>(n, 1ull << 22);
+  uint8_t* stage = nullptr;
+  int* derr = nullptr;
+  FB_CUDA(cudaMalloc(&stage, chunk * SZ));
+  FB_CUDA(cudaMalloc(&derr, 4));
+  FB_CUDA(cudaMemsetAsync(derr, 0, 4, st));
+  for (uint64_t off = 0; off < n; off += chunk) {
+    uint64_t cnt = std::min(chunk, n - off);
+    FB_CUDA(cudaMemcpyAsync(stage, host_be + off * SZ, cnt * SZ, cudaMemcpyHostToDevice, st));
+    unsigned blocks = (unsigned)std::min<uint64_t>((cnt + 127) / 128, 148 * 16);
+    kernel<<<blocks, 128, 0, st>>>(stage, cnt, dev_out + off, checked, derr);
+    FB_CUDA(cudaStreamSynchronize(st));
+  }
+  int herr = 0;
+  FB_CUDA(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+  cudaFree(stage);
+  cudaFree(derr);
+  if (herr) {
+    set_error("invalid point in Parameters (%s)",
+              herr == 1 ? "coordinate not in field" : herr == 2 ? "not on curve" : "bad flag bits");
+    return FB_ERR_FORMAT;
+  }
+  return FB_OK;
+}
+
+int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, bool checked, cudaStream_t st) {
+  return decode_points<G1Affine, 64>(host_be, n, dev_out, checked, st, k_decode_g1);
+}
+int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, bool checked, cudaStream_t st) {
+  return decode_points<G2Affine, 128>(host_be, n, dev_out, checked, st, k_decode_g2);
+}
+int host_decode_g1(const uint8_t* be, G1Affine& out) { return decode_g1(be, out, true); }
+int host_decode_g2(const uint8_t* be, G2Affine& out) { return decode_g2(be, out, true); }
+
+void host_encode_g1(const G1Affine& p, uint8_t* be) {
+  memset(be, 0, 64);
+  if (p.is_inf()) { be[0] = 0x40; return; }
+  Fq x = from_mont(p.x), y = from_mont(p.y);
+  limbs_to_be(x.v, be);
+  limbs_to_be(y.v, be + 32);
+}
+void host_encode_g2(const G2Affine& p, uint8_t* be) {
+  memset(be, 0, 128);
+  if (p.is_inf()) { be[0] = 0x40; return; }
+  Fq c[4] = {from_mont(p.x.c1), from_mont(p.x.c0), from_mont(p.y.c1), from_mont(p.y.c0)};
+  for (int i = 0; i < 4; i++) limbs_to_be(c[i].v, be + 32 * i);
+}
+
+}  // namespace fb

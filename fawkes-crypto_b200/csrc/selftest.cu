@@ -1,0 +1,264 @@
+// Test / micro-benchmark entry points (fb_test_*, fb_probe_*): each drives one kernel
+// family on caller-supplied host buffers so tests can compare against the CPU oracle
+// through the C ABI.  Not part of the reference interface.
+#include "../../include/fawkes_b200.h"
+
+#include <cstring>
+
+#include "internal.h"
+
+namespace fb {
+
+template <class C>
+__global__ void k_field_op(int op, const Fp<C>* a, const Fp<C>* b, Fp<C>* out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    Fp<C> x = a[i], y = b ? b[i] : Fp<C>::zero(), r;
+    switch (op) {
+      case 0: r = mul(x, y); break;
+      case 1: r = add(x, y); break;
+      case 2: r = sub(x, y); break;
+      case 3: r = inv(x); break;
+      default: r = mul_c(x, y); break;
+    }
+    out[i] = r;
+  }
+}
+
+// dependent-free IMAD.WIDE accumulate streams: 8 independent accumulators per thread
+__global__ void k_probe_imad(uint64_t* out, uint32_t seed, int iters) {
+  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  uint64_t acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
+    }
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= acc[j];
+  if (s == 0x1234567812345678ull) out[0] = s;  // keep the loop alive
+}
+
+__global__ void k_probe_fr_mul(Fr* out, int iters) {
+  Fr x = Fr::one(), y = Fr::r2();
+  x.v[0] += threadIdx.x;
+  y.v[1] ^= blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+    x = mul(x, y);
+    y = mul(y, x);
+  }
+  if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
+}
+
+template <class F>
+__global__ void k_xyzz_to_affine(const XYZZ<F>* in, Affine<F>* out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = to_affine(in[i]);
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_test_field(fb_ctx* ctx_, int field, int op, const uint64_t* a, const uint64_t* b,
+                  uint64_t* out, uint64_t n) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !a || !out) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  void *da, *db = nullptr, *dout;
+  FB_CUDA(cudaMalloc(&da, n * 32));
+  FB_CUDA(cudaMalloc(&dout, n * 32));
+  FB_CUDA(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+  if (b) {
+    FB_CUDA(cudaMalloc(&db, n * 32));
+    FB_CUDA(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+  }
+  unsigned blocks = (unsigned)std::min<uint64_t>((n + 127) / 128, 148 * 8);
+  if (field == 0)
+    k_field_op<FrCfg><<<blocks, 128, 0, ctx->stream>>>(op, (const Fr*)da, (const Fr*)db, (Fr*)dout, n);
+  else
+    k_field_op<FqCfg><<<blocks, 128, 0, ctx->stream>>>(op, (const Fq*)da, (const Fq*)db, (Fq*)dout, n);
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  FB_CUDA(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return FB_OK;
+}
+
+int fb_test_ntt(fb_ctx* ctx_, int log_n, int kind, uint64_t* data) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !data || kind < 0 || kind > 3) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  NttDomain dom;
+  if (dom.init(log_n, ctx->stream) != 0) { set_error("domain init failed"); return FB_ERR_DOMAIN; }
+  Fr *x, *scratch;
+  size_t bytes = sizeof(Fr) << log_n;
+  FB_CUDA(cudaMalloc(&x, bytes));
+  FB_CUDA(cudaMalloc(&scratch, bytes));
+  FB_CUDA(cudaMemcpyAsync(x, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  dom.transform(x, scratch, kind, ctx->stream);
+  FB_CUDA(cudaMemcpyAsync(data, x, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  FB_CUDA(cudaGetLastError());
+  cudaFree(x); cudaFree(scratch);
+  dom.destroy();
+  return FB_OK;
+}
+
+int fb_test_h(fb_ctx* ctx_, int log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+              uint64_t* out, float* ms) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !a || !b || !c) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  NttDomain dom;
+  if (dom.init(log_n, st) != 0) { set_error("domain init failed"); return FB_ERR_DOMAIN; }
+  const size_t bytes = sizeof(Fr) << log_n;
+  Fr *ev[3], *scratch;
+  const uint64_t* src[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) FB_CUDA(cudaMalloc(&ev[i], bytes));
+  FB_CUDA(cudaMalloc(&scratch, bytes));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  const int reps = ms ? 3 : 1;
+  for (int rep = 0; rep < reps; rep++) {
+    for (int i = 0; i < 3; i++) FB_CUDA(cudaMemcpyAsync(ev[i], src[i], bytes, cudaMemcpyHostToDevice, st));
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < 3; i++) dom.ifft_then_coset_fft(ev[i], st);
+    dom.pointwise_then_icoset_fft(ev[0], ev[1], ev[2], st);
+    cudaEventRecord(e1, st);
+    FB_CUDA(cudaStreamSynchronize(st));
+    float t;
+    cudaEventElapsedTime(&t, e0, e1);
+    best = std::min(best, t);
+  }
+  if (ms) *ms = best;
+  if (out) {
+    dom.bitrev(scratch, ev[0], st);
+    FB_CUDA(cudaMemcpyAsync(out, scratch, bytes - sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+  }
+  FB_CUDA(cudaGetLastError());
+  for (int i = 0; i < 3; i++) cudaFree(ev[i]);
+  cudaFree(scratch);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  dom.destroy();
+  return FB_OK;
+}
+
+int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_t* scalars,
+                uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !bases_raw || !scalars || !result_raw || (group != 1 && group != 2) || n == 0 ||
+      n >= (1ull << 31))
+    return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t psz = group == 1 ? 64 : 128;
+  void *dbases, *dres, *daff;
+  Fr* dsc;
+  FB_CUDA(cudaMalloc(&dbases, n * psz));
+  FB_CUDA(cudaMalloc(&dsc, n * 32));
+  FB_CUDA(cudaMalloc(&dres, sizeof(G2XYZZ)));
+  FB_CUDA(cudaMalloc(&daff, sizeof(G2Affine)));
+  FB_CUDA(cudaMemcpy(dbases, bases_raw, n * psz, cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpy(dsc, scalars, n * 32, cudaMemcpyHostToDevice));
+  MsmPlan plan = MsmPlan::make((uint32_t)n);
+  MsmScratch scr;
+  if (scr.alloc(n, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  if (reps < 1) reps = 1;
+  float best = 1e30f;
+  int rc = 0;
+  for (int rep = 0; rep < reps && !rc; rep++) {
+    cudaEventRecord(e0, st);
+    if (group == 1) rc = msm_g1((const G1Affine*)dbases, dsc, nullptr, plan, scr, (G1XYZZ*)dres, false, st);
+    else rc = msm_g2((const G2Affine*)dbases, dsc, nullptr, plan, scr, (G2XYZZ*)dres, false, st);
+    cudaEventRecord(e1, st);
+    FB_CUDA(cudaStreamSynchronize(st));
+    float t;
+    cudaEventElapsedTime(&t, e0, e1);
+    best = std::min(best, t);
+  }
+  if (rc) { set_error("msm failed %d", rc); return FB_ERR_CUDA; }
+  if (ms_per_rep) *ms_per_rep = best;
+  if (group == 1) k_xyzz_to_affine<Fq><<<1, 1, 0, st>>>((const G1XYZZ*)dres, (G1Affine*)daff, 1);
+  else k_xyzz_to_affine<Fq2><<<1, 1, 0, st>>>((const G2XYZZ*)dres, (G2Affine*)daff, 1);
+  FB_CUDA(cudaMemcpyAsync(result_raw, daff, psz, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
+  cudaFree(dbases); cudaFree(dsc); cudaFree(dres); cudaFree(daff);
+  scr.release();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FB_OK;
+}
+
+int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !mac_per_s) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  uint64_t* d;
+  FB_CUDA(cudaMalloc(&d, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 4096, blocks = 148 * 8, threads = 256;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_probe_imad<<<blocks, threads, 0, ctx->stream>>>(d, 12345u + rep, iters);
+    cudaEventRecord(e1, ctx->stream);
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double rate = (double)blocks * threads * iters * 8 / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  *mac_per_s = best;
+  cudaFree(d);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FB_OK;
+}
+
+int fb_probe_fr_mul(fb_ctx* ctx_, double* mul_per_s) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !mul_per_s) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  Fr* d;
+  FB_CUDA(cudaMalloc(&d, 32));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 512, blocks = 148 * 8, threads = 256;
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_probe_fr_mul<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+    cudaEventRecord(e1, ctx->stream);
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double rate = (double)blocks * threads * iters * 2 / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  *mul_per_s = best;
+  cudaFree(d);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+/* fawkes_b200.h -- C ABI of the B200-native Groth16 proving backend.
+ *
+ * Drop-in boundary for fawkes_crypto::backend::bellman_groth16: these entry points
+ * are what a Rust FFI crate binds in place of the bellman_ce calls made by the
+ * reference (paths relative to the fawkes-crypto repository root):
+ *
+ *   fb_pk_load / fb_pk_load_circuit
+ *       <- bellman::groth16::Parameters::read + WitnessCS::get_gate_iterator
+ *          fawkes-crypto/src/backend/bellman_groth16/mod.rs:159-175
+ *          fawkes-crypto/src/circuit/r1cs/cs.rs:184-223,248-250
+ *   fb_prove
+ *       <- bellman::groth16::create_random_proof(bcs, &params.0, rng)
+ *          fawkes-crypto/src/backend/bellman_groth16/prover.rs:78-80
+ *          (with BellmanCS::synthesize, mod.rs:61-102, folded in: the witness
+ *          vectors cross as the raw `Vec<Num<Fr>>` buffers of WitnessCS, cs.rs:99-102)
+ *   fb_setup
+ *       <- bellman::groth16::generate_random_parameters(bcs, rng)
+ *          fawkes-crypto/src/backend/bellman_groth16/setup.rs:17-20
+ *   fb_verify
+ *       <- bellman::groth16::{prepare_verifying_key, verify_proof}
+ *          fawkes-crypto/src/backend/bellman_groth16/verifier.rs:75-81
+ *
+ * Conventions
+ *   - Every field element is a `Num<Fp>` as it sits in memory: 4 x u64 little-endian
+ *     limbs in MONTGOMERY form (ff-uint/src/num/mod.rs:21-23); r and s likewise.
+ *   - Raw points are `G1Point`/`G2Point` as they sit in memory
+ *     (backend/bellman_groth16/group.rs:53-123): G1 = x|y (64 B), G2 = x.c0|x.c1|y.c0|y.c1
+ *     (128 B); the point at infinity is all-zero.
+ *   - `bellman_params` is the byte string written by bellman's Parameters::write, i.e.
+ *     `Parameters.0` of mod.rs:139 (big-endian uncompressed points, u32 BE lengths).
+ *   - All functions return 0 on success or a negative FB_ERR_* code; fb_last_error()
+ *     gives a thread-local message.  The reference panics (`.unwrap()`, prover.rs:80,
+ *     setup.rs:20, verifier.rs:80) or returns io::Error (mod.rs:166-167); the Rust shim
+ *     maps codes back to those behaviours.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with FB_ERR_CUDA.  fb_verify is host code, as in the reference.
+ *   - One host thread per fb_ctx; calls are synchronous (prover.rs:63-90 is blocking).
+ */
+#ifndef FAWKES_B200_H
+#define FAWKES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_OK 0
+#define FB_ERR_ARG (-1)
+#define FB_ERR_CUDA (-2)
+#define FB_ERR_FORMAT (-3)
+#define FB_ERR_DOMAIN (-4)   /* bellman SynthesisError::PolynomialDegreeTooLarge */
+#define FB_ERR_IDENTITY (-5) /* bellman SynthesisError::UnexpectedIdentity */
+#define FB_ERR_DENSITY (-6)  /* query length != structural density of the circuit */
+#define FB_ERR_VK (-7)       /* bellman SynthesisError::MalformedVerifyingKey */
+
+typedef struct fb_ctx fb_ctx;         /* one device + its streams */
+typedef struct fb_pk fb_pk;           /* HBM-resident proving key + CSR + workspaces */
+typedef struct fb_circuit fb_circuit; /* host-side R1CS in CSR form (parsed gate blob) */
+
+typedef struct fb_pk_info {
+  uint32_t n_in;      /* inputs incl. ONE */
+  uint32_t n_aux;
+  uint32_t n_gates;   /* rows before bellman's input rows */
+  uint32_t log_m;     /* domain size 2^log_m */
+  uint32_t len_h, len_l, len_a, len_b;
+  uint64_t nnz;       /* total non-zeros of A,B,C */
+  uint64_t hbm_bytes; /* device memory held by the key */
+} fb_pk_info;
+
+/* ---- context --------------------------------------------------------------- */
+int fb_init(const int* devices, int ndev, fb_ctx** out); /* ndev must be 1: one process per GPU */
+void fb_shutdown(fb_ctx* ctx);
+const char* fb_last_error(void);
+int fb_device_count(void);
+void fb_free(void* p); /* for buffers returned by fb_setup */
+
+/* ---- circuit (parsed gate stream) ------------------------------------------ */
+/* gates_brotli: `Parameters.2` (setup.rs:25-32); num_gates: `Parameters.1`. */
+int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_gates,
+                          uint32_t n_in, uint32_t n_aux, fb_circuit** out);
+/* same, from the un-compressed borsh gate stream */
+int fb_circuit_from_raw_gates(const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
+                              uint32_t n_aux, fb_circuit** out);
+void fb_circuit_free(fb_circuit* c);
+int fb_circuit_shape(const fb_circuit* c, uint32_t* n_in, uint32_t* n_aux, uint32_t* n_gates,
+                     uint64_t* nnz);
+
+/* ---- proving key ----------------------------------------------------------- */
+int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uint8_t* gates_brotli,
+               size_t glen, uint32_t num_gates, int checked, fb_pk** out);
+int fb_pk_load_circuit(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
+                       const fb_circuit* circuit, int checked, fb_pk** out);
+/* Multi-GPU: this process keeps only base indices [shard, shard+1) * len / nshards of each
+ * query (h, l, a, b_g1, b_g2).  fb_prove_partial then returns partial sums. */
+int fb_pk_load_shard(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
+                     const fb_circuit* circuit, int checked, int shard, int nshards, fb_pk** out);
+void fb_pk_free(fb_pk* pk);
+int fb_pk_get_info(const fb_pk* pk, fb_pk_info* info);
+
+/* ---- prove ------------------------------------------------------------------ */
+/* inputs[n_in][4] with inputs[0] = ONE (cs.rs:111); aux[n_aux][4]; r, s: Num<Fr>.
+ * proof_raw: a.x a.y | b.x.c0 b.x.c1 b.y.c0 b.y.c1 | c.x c.y  (== Proof in memory,
+ * prover.rs:13-17).  h_out: optional [m-1][4] H coefficients (natural order), or NULL. */
+int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
+             uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
+             uint64_t* h_out);
+/* Same, host buffers already on the device (dev_w = [inputs | aux] as Num<Fr>). */
+int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
+                    const uint64_t s[4], uint8_t proof_raw[256]);
+/* Sharded prove: partial[5] raw affine sums in the order h, l, a, b_g1 (64 B each, slots of
+ * 128 B) and b_g2 (128 B): 5 x 128 B.  Combine with fb_prove_finish on any rank. */
+int fb_prove_partial(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in,
+                     const uint64_t* aux, uint32_t n_aux, uint8_t partial[640]);
+int fb_prove_finish(const fb_pk* pk, const uint8_t* partials, int nparts, const uint64_t r[4],
+                    const uint64_t s[4], uint8_t proof_raw[256]);
+/* device-time breakdown of the last fb_prove on this key, milliseconds:
+ * [0] h2d  [1] r1cs eval  [2] H pipeline (7 NTTs)  [3] MSMs  [4] d2h+assembly (host)  [5] total */
+int fb_prove_timings(const fb_pk* pk, float ms[6]);
+
+/* ---- setup / verify ---------------------------------------------------------- */
+/* trapdoor = alpha, beta, gamma, delta, tau (Num<Fr>); generators = the standard BN254
+ * ones.  Writes bellman-format Parameters bytes (free with fb_free). */
+int fb_setup(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4],
+             uint8_t** params_out, size_t* len);
+/* vk: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 raw (64+128+128+128 B) then n_ic raw G1 (VK of
+ * verifier.rs:12-18 in memory).  inputs: public inputs WITHOUT the leading ONE. */
+int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t proof_raw[256],
+              const uint64_t* inputs, uint32_t n_inputs, int* ok);
+
+/* ---- benchmark / test harness ------------------------------------------------ */
+/* Synthetic random R1CS of SURVEY.md section 8(d).  Witness buffers stay owned by the circuit. */
+int fb_circuit_synth(uint64_t n_rows, uint64_t seed, fb_circuit** out);
+int fb_circuit_witness(const fb_circuit* c, const uint64_t** inputs, const uint64_t** aux);
+int fb_synth_trapdoor(uint64_t seed, uint64_t out[7][4]); /* alpha beta gamma delta tau r s */
+/* op: 0 mul 1 add 2 sub 3 inv 4 portable-C mul; field: 0 Fr 1 Fq; host buffers [n][4] */
+int fb_test_field(fb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b,
+                  uint64_t* out, uint64_t n);
+/* kind 0 fft 1 ifft 2 coset_fft 3 icoset_fft on 2^log_n host elements, natural order */
+int fb_test_ntt(fb_ctx* ctx, int log_n, int kind, uint64_t* data);
+/* H coefficients from row evaluations a,b,c (each [2^log_n][4]); out [2^log_n - 1][4] */
+int fb_test_h(fb_ctx* ctx, int log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+              uint64_t* out, float* ms);
+/* MSM on host buffers: group 1 (bases 64 B) or 2 (128 B); result raw affine; reps>1 times it */
+int fb_test_msm(fb_ctx* ctx, int group, const uint8_t* bases_raw, const uint64_t* scalars,
+                uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep);
+/* bases[i] = k_i * G (fixed-base kernel used by setup), raw affine out */
+int fb_test_fixed_base(fb_ctx* ctx, int group, const uint64_t* scalars, uint64_t n,
+                       uint8_t* out_raw);
+/* IMAD-pipe roofline probe: returns 32x32->64 multiply-accumulates per second */
+int fb_probe_imad(fb_ctx* ctx, double* mac_per_s);
+/* Fr multiplies per second (register resident, dependent chains across many warps) */
+int fb_probe_fr_mul(fb_ctx* ctx, double* mul_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAWKES_B200_H */
