@@ -167,7 +167,8 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   PK_CUDA(cudaMalloc(&pk->a, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
   PK_TRY(decode_g1_be(v.a + lo * 64, cnt, pk->a, checked, st));
   PK_CUDA(cudaMalloc(&pk->a_map, std::max<uint64_t>(cnt, 1) * 4));
-  PK_CUDA(cudaMemcpy(pk->a_map, a_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice));
+  PK_CUDA(cudaMemcpyAsync(pk->a_map, a_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice, st));
+  PK_CUDA(cudaStreamSynchronize(st));
   slice(v.n_b1, lo, cnt);
   pk->len_b = (uint32_t)cnt;
   PK_CUDA(cudaMalloc(&pk->b1, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
@@ -175,7 +176,8 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   PK_CUDA(cudaMalloc(&pk->b2, std::max<uint64_t>(cnt, 1) * sizeof(G2Affine)));
   PK_TRY(decode_g2_be(v.b2 + lo * 128, cnt, pk->b2, checked, st));
   PK_CUDA(cudaMalloc(&pk->b_map, std::max<uint64_t>(cnt, 1) * 4));
-  PK_CUDA(cudaMemcpy(pk->b_map, b_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice));
+  PK_CUDA(cudaMemcpyAsync(pk->b_map, b_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice, st));
+  PK_CUDA(cudaStreamSynchronize(st));
   // CSR + domain + workspaces
   PK_TRY(upload_csr(csr, pk->csr, st));
   if (pk->dom.init(k, st) != 0) {

@@ -266,7 +266,8 @@ static int decode_points(const uint8_t* host_be, uint64_t n, P* dev_out, bool ch
     FB_CUDA(cudaStreamSynchronize(st));
   }
   int herr = 0;
-  FB_CUDA(cudaMemcpy(&herr, derr, 4, cudaMemcpyDeviceToHost));
+  FB_CUDA(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
   cudaFree(stage);
   cudaFree(derr);
   if (herr) {

@@ -75,18 +75,19 @@ int fb_test_field(fb_ctx* ctx_, int field, int op, const uint64_t* a, const uint
   void *da, *db = nullptr, *dout;
   FB_CUDA(cudaMalloc(&da, n * 32));
   FB_CUDA(cudaMalloc(&dout, n * 32));
-  FB_CUDA(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (b) {
     FB_CUDA(cudaMalloc(&db, n * 32));
-    FB_CUDA(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+    FB_CUDA(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   }
   unsigned blocks = (unsigned)std::min<uint64_t>((n + 127) / 128, 148 * 8);
   if (field == 0)
     k_field_op<FrCfg><<<blocks, 128, 0, ctx->stream>>>(op, (const Fr*)da, (const Fr*)db, (Fr*)dout, n);
   else
     k_field_op<FqCfg><<<blocks, 128, 0, ctx->stream>>>(op, (const Fq*)da, (const Fq*)db, (Fq*)dout, n);
+  FB_CUDA(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   FB_CUDA(cudaStreamSynchronize(ctx->stream));
-  FB_CUDA(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+  FB_CUDA(cudaGetLastError());
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return FB_OK;
 }
@@ -170,8 +171,8 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   FB_CUDA(cudaMalloc(&dsc, n * 32));
   FB_CUDA(cudaMalloc(&dres, sizeof(G2XYZZ)));
   FB_CUDA(cudaMalloc(&daff, sizeof(G2Affine)));
-  FB_CUDA(cudaMemcpy(dbases, bases_raw, n * psz, cudaMemcpyHostToDevice));
-  FB_CUDA(cudaMemcpy(dsc, scalars, n * 32, cudaMemcpyHostToDevice));
+  FB_CUDA(cudaMemcpyAsync(dbases, bases_raw, n * psz, cudaMemcpyHostToDevice, st));
+  FB_CUDA(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, st));
   MsmPlan plan = MsmPlan::make((uint32_t)n);
   MsmScratch scr;
   if (scr.alloc(n, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
