@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Groth16 prove benchmark on synthetic random R1CS (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-rows 20] [--impl ours|reference]
+
+A step = one Groth16 prove of the synthetic circuit of SURVEY.md section 8(d) with
+2^log_rows rows (default 2^20 = BASELINE.json configs[2]; --log-rows 24 = configs[3]).
+  value  = seconds per prove with the witness already resident in HBM (fb_prove_device)
+  e2e    = seconds per prove through the reference-facing call fb_prove with HOST buffers
+           (pinned witness -> H2D inside the timed region, 256-byte proof read back)
+  N > 1  : one process per GPU (torchrun); bases sharded by index (fb_pk_load_shard), every
+           rank proves its shard, the five partial sums are all-gathered over NCCL and rank 0
+           assembles -- strong scaling of ONE proof.
+--impl reference times the CPU restatement of the reference prover (oracle/cpu_prover.cpp;
+the Rust reference cannot be built in this image) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_BASE = 0xFA3CE50000
+MAC32_PER_MIXED_ADD = 10 * 136      # XYZZ madd: 8M + 2S, 136 32x32 MACs per Montgomery multiply
+BYTES_PER_MIXED_ADD_G1 = 64 + 4     # one affine base + one sorted index
+BYTES_PER_MIXED_ADD_G2 = 128 + 4
+
+
+def cfg_number(log_rows: int) -> int:
+    return {20: 3, 24: 4}.get(log_rows, 100 + log_rows)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------- CPU arm ---
+def expand_csr(fb, circ):
+    """CSR views of the product's circuit -> (rowptr, col, coef[nnz,4]) for the CPU oracle."""
+    lib = fb.native.lib
+    rowptr, col, coef = [], [], []
+    sh = circ.shape()
+    one = np.frombuffer((((1 << 256) % fb.groth16.FR_MOD)).to_bytes(32, "little"), dtype=np.uint64)
+    mone = np.frombuffer(((fb.groth16.FR_MOD - (1 << 256) % fb.groth16.FR_MOD)).to_bytes(32, "little"), dtype=np.uint64)
+    for m in range(3):
+        prp, pcl, pci, pct = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nnz, ncoef = C.c_uint64(), C.c_uint64()
+        fb.native.check(lib.fb_circuit_csr(circ.handle, m, C.byref(prp), C.byref(pcl), C.byref(pci), C.byref(nnz),
+                                           C.byref(pct), C.byref(ncoef)))
+        as_u32 = lambda p, n: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(n,))
+        rp = as_u32(prp, sh["n_gates"] + 1).copy()
+        cl = as_u32(pcl, nnz.value).copy() if nnz.value else np.zeros(0, np.uint32)
+        ci = as_u32(pci, nnz.value).copy() if nnz.value else np.zeros(0, np.uint32)
+        table = np.zeros((ncoef.value + 2, 4), dtype=np.uint64)
+        table[0], table[1] = one, mone
+        if ncoef.value:
+            table[2:] = np.ctypeslib.as_array(C.cast(pct, C.POINTER(C.c_uint64)), shape=(ncoef.value, 4))
+        rowptr.append(rp)
+        col.append(cl)
+        coef.append(table[ci])
+    return rowptr, col, coef
+
+
+def make_case(fb, ctx, log_rows: int):
+    """Synthetic circuit + witness + trapdoor + Parameters (setup runs on the GPU, untimed)."""
+    seed = SEED_BASE + cfg_number(log_rows)
+    circ = fb.Circuit.synthetic(1 << log_rows, seed)
+    td = np.zeros((7, 4), dtype=np.uint64)
+    fb.native.check(fb.native.lib.fb_synth_trapdoor(seed, td.ctypes.data))
+    tdi = [fb.groth16.fr_unraw(x) for x in td]
+    t0 = time.time()
+    params = fb.setup(circ, ctx, trapdoor=tdi[:5])
+    return circ, params, tdi, time.time() - t0
+
+
+def cpu_prove_once(fb, circ, params, tdi, nthreads):
+    from oracle import cpu
+    sh = circ.shape()
+    rp, cl, cf = expand_csr(fb, circ)
+    wi, wa = circ.witness()
+    r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
+    proof, _, st = cpu.prove(params.bellman_bytes, sh["n_gates"], sh["n_in"], sh["n_aux"], rp, cl, cf, wi, wa, r, s,
+                             nthreads)
+    return proof, st
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fawkes_crypto_b200 as fb
+    from oracle import cpu
+    cores = cpu.hw_threads()
+    sample_log = min(args.log_rows, args.ref_sample_log)
+    ctx = fb.Context(0)   # parameter generation only (untimed); the timed path is pure CPU
+    circ, params, tdi, _ = make_case(fb, ctx, sample_log)
+    sh = circ.shape()
+    rp, cl, cf = expand_csr(fb, circ)
+    wi, wa = circ.witness()
+    r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
+    scale = float(1 << (args.log_rows - sample_log))
+    times = []
+    proof = None
+    for i in range(args.warmup + args.steps):
+        proof, _, st = cpu.prove(params.bellman_bytes, sh["n_gates"], sh["n_in"], sh["n_aux"], rp, cl, cf, wi, wa, r, s,
+                                 cores)
+        if i >= args.warmup:
+            times.append(st[3])
+    ok = fb.verify(params.get_vk(), fb.Proof.from_raw(proof), wi[1:])
+    sec = float(np.mean(times)) * scale
+    sample = (f"full prove of the synthetic 2^{sample_log}-row circuit per step"
+              + (f", time scaled x{int(scale)} to 2^{args.log_rows} rows (prove cost ~linear in rows)" if scale > 1 else ""))
+    line = {
+        "impl": "reference", "metric": "groth16_prove_time_s", "value": sec, "unit": "s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (256-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"synthetic random R1CS 2^{args.log_rows} rows, BN254 Groth16 prove, fixed r,s",
+                   "log_rows": args.log_rows},
+        "cpu_baseline": {"value": sec, "unit": "s", "cores": cores, "kind": "port", "sample": sample,
+                         "proof_verifies": bool(ok),
+                         "note": "C++ restatement of bellman_ce's prover shape; the Rust reference cannot be built here"},
+        "e2e": {"value": sec, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm ---
+def run_ours(args):
+    import torch
+    import fawkes_crypto_b200 as fb
+    lib = fb.native.lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = fb.Context(local)
+    circ, params, tdi, setup_s = make_case(fb, ctx, args.log_rows)
+    sh = circ.shape()
+    pk = params.load(ctx, checked=False, shard=rank, nshards=world)
+    info = params.info()
+    wi, wa = circ.witness()
+    n_in, n_aux = sh["n_in"], sh["n_aux"]
+    # pinned host witness (e2e source) and device-resident copy (value source)
+    w_host = torch.empty((n_in + n_aux, 4), dtype=torch.int64).pin_memory()
+    w_np = w_host.numpy().view(np.uint64)
+    w_np[:n_in] = wi
+    w_np[n_in:] = wa
+    w_dev = w_host.to(f"cuda:{local}")
+    r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
+    proof = np.zeros(256, dtype=np.uint8)
+    partial = np.zeros(640, dtype=np.uint8)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    gathered = torch.empty((world, 640), dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
+
+    def step(device_resident: bool):
+        if world == 1:
+            if device_resident:
+                fb.native.check(lib.fb_prove_device(ctx.handle, pk, w_dev.data_ptr(), r.ctypes.data, s.ctypes.data,
+                                                    proof.ctypes.data))
+            else:
+                fb.native.check(lib.fb_prove(ctx.handle, pk, w_np.ctypes.data, n_in, w_np[n_in:].ctypes.data, n_aux,
+                                             r.ctypes.data, s.ctypes.data, proof.ctypes.data, None))
+        else:
+            import torch.distributed as dist
+            # every rank evaluates the circuit and H (replicated), MSMs are sharded by base index
+            fb.native.check(lib.fb_prove_partial(ctx.handle, pk, w_np.ctypes.data, n_in, w_np[n_in:].ctypes.data,
+                                                 n_aux, partial.ctypes.data))
+            mine = torch.from_numpy(partial).to(f"cuda:{local}")
+            dist.all_gather_into_tensor(gathered, mine)
+            if rank == 0:
+                parts = gathered.cpu().numpy()
+                fb.native.check(lib.fb_prove_finish(fb.native.ptr(params.bellman_bytes), len(params.bellman_bytes),
+                                                    parts.ctypes.data, world, r.ctypes.data, s.ctypes.data,
+                                                    proof.ctypes.data))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(device_resident: bool, steps: int) -> float:
+        total = 0.0
+        for _ in range(steps):
+            flush.zero_()            # evict L2 between timed iterations
+            barrier()
+            t0 = time.perf_counter()
+            step(device_resident)
+            barrier()
+            total += time.perf_counter() - t0
+        t = torch.tensor([total], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step(True)
+    barrier()
+    lib.fb_kernel_stats_enable(1)
+    lib.fb_kernel_stats_reset()
+    launches0 = lib.fb_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    stage = {k: 0.0 for k in ("h2d", "r1cs", "h_ntt", "msm", "host", "total")}
+    t_value = 0.0
+    for _ in range(args.steps):
+        t_value += timed(True, 1)
+        for k_, v in params.timings().items():
+            stage[k_] += v / args.steps
+    clocks = sampler.stop()
+    launches = (lib.fb_launch_count() - launches0) / args.steps
+    kst = {}
+    for which, name in ((0, "msm_g1_accumulate"), (1, "msm_g2_accumulate"), (2, "ntt_pass")):
+        n, ms = C.c_uint64(), C.c_double()
+        fb.native.check(lib.fb_kernel_stats(which, C.byref(n), C.byref(ms)))
+        kst[name] = {"launches": n.value, "total_ms": ms.value}
+    lib.fb_kernel_stats_enable(0)
+    t_e2e = timed(False, args.steps)
+    ok = True
+    if rank == 0:
+        ok = fb.verify(params.get_vk(), fb.Proof.from_raw(proof.tobytes()), wi[1:])
+    if rank != 0:
+        return
+    sec = t_value / args.steps
+    sec_e2e = t_e2e / args.steps
+
+    # ---- roofline of the dominant kernel: G1 bucket accumulation (4 launches per prove) ----
+    peaks = load_peaks()
+    W = -(-255 // info["msm_window_bits"])
+    g1 = kst["msm_g1_accumulate"]
+    adds_per_prove = info["g1_digit_slots"]
+    per_launch_adds = adds_per_prove / 4.0
+    avg_ms = g1["total_ms"] / max(g1["launches"], 1)
+    ach_gbs = per_launch_adds * BYTES_PER_MIXED_ADD_G1 / (avg_ms * 1e-3) / 1e9 if avg_ms else 0.0
+    imad = C.c_double()
+    fb.native.check(lib.fb_probe_imad(ctx.handle, C.byref(imad)))
+    ach_mac = per_launch_adds * MAC32_PER_MIXED_ADD / (avg_ms * 1e-3) if avg_ms else 0.0
+    roofline = {"kernel": "k_accumulate<Fq> (G1 bucket accumulation)", "bound": "hbm", "achieved": ach_gbs,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peaks["source"], "avg_launch_ms": avg_ms, "launches_timed": g1["launches"],
+                "algorithmic_bytes_per_launch": per_launch_adds * BYTES_PER_MIXED_ADD_G1,
+                "note": "algorithmic bytes = (64 B base + 4 B index) x n x W digits; the kernel is integer-pipe "
+                        "bound, see roofline_imad"}
+    roofline_imad = {"kernel": roofline["kernel"], "bound": "imad", "achieved": ach_mac / 1e12,
+                     "peak": imad.value / 1e12, "unit": "T MAC32/s", "frac": ach_mac / imad.value if imad.value else None,
+                     "peak_source": "measured live: dependent-free mad.wide.u32 streams (fb_probe_imad)",
+                     "algorithmic_mac32_per_launch": per_launch_adds * MAC32_PER_MIXED_ADD}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu
+        cores = cpu.hw_threads()
+        sl = min(args.log_rows, args.cpu_sample_log)
+        if sl == args.log_rows:
+            c2, p2, td2 = circ, params, tdi
+        else:
+            c2, p2, td2, _ = make_case(fb, ctx, sl)
+        cproof, st = cpu_prove_once(fb, c2, p2, td2, cores)
+        scale = float(1 << (args.log_rows - sl))
+        same = None
+        if sl == args.log_rows:
+            same = bool(cproof == proof.tobytes())
+        cpu_baseline = {"value": st[3] * scale, "unit": "s", "cores": cores, "kind": "port",
+                        "sample": f"one full CPU prove of the synthetic 2^{sl}-row circuit"
+                                  + (f", scaled x{int(scale)}" if scale > 1 else ""),
+                        "stages_s": {"eval": st[0], "fft": st[1], "multiexp": st[2]},
+                        "proof_bytes_equal_gpu": same}
+
+    line = {
+        "metric": "groth16_prove_time_s", "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32 limbs (256-bit modular integers)", "data": "synthetic",
+        "config": {"workload": f"synthetic random R1CS 2^{args.log_rows} rows, BN254 Groth16 prove, fixed r,s",
+                   "log_rows": args.log_rows, "n_aux": n_aux, "nnz": sh["nnz"], "domain_log2": info["log_m"],
+                   "parallelism": f"msm-base-shard x{world}" if world > 1 else "single GPU",
+                   "l2": "256 MiB buffer written between timed iterations; working set also exceeds L2",
+                   "timing": "host clock around the synchronous C-ABI call, cuda synchronize + barrier on both "
+                             "sides, max over ranks; stage_ms from CUDA events on the launching stream"},
+        "clocks": clocks,
+        "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": int((n_in + n_aux) * 32),
+                "d2h_bytes_per_step": 256 + 5 * 256},
+        "gpu_launches": launches,
+        "roofline": roofline, "roofline_imad": roofline_imad,
+        "stage_ms": stage, "kernel_ms": kst,
+        "g1_msm_mpoints_per_s": (adds_per_prove / W) / (g1["total_ms"] / args.steps * 1e-3) / 1e6 if g1["total_ms"] else None,
+        "proof_verifies": bool(ok), "setup_s": setup_s, "pk_hbm_bytes": info["hbm_bytes"],
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-rows", type=int, default=int(os.environ.get("FB_BENCH_LOG_ROWS", "20")))
+    ap.add_argument("--cpu-sample-log", type=int, default=18,
+                    help="CPU baseline proves 2^this rows (scaled) so the default run stays within minutes")
+    ap.add_argument("--ref-sample-log", type=int, default=17)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

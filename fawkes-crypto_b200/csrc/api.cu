@@ -9,6 +9,9 @@
 
 namespace fb {
 const char* last_error_cstr();
+void kstat_enable(bool on);
+void kstat_reset();
+void kstat_collect(int kind, unsigned long long* launches, double* ms);
 
 static uint32_t be32(const uint8_t* p) {
   return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
@@ -220,7 +223,11 @@ static void fr_canonical(const uint64_t x[4], uint32_t out[8]) {
 
 // SURVEY.md App. C.5:  A = alpha + r*delta + sum_a ;  B = beta2 + s*delta2 + sum_b2 ;
 // C = rs*delta + s*alpha + r*beta1 + s*sum_a + r*sum_b1 + sum_h + sum_l
-static int assemble(const ProvingKey* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
+struct VkPoints {
+  G1Affine alpha_g1, beta_g1, delta_g1;
+  G2Affine beta_g2, delta_g2;
+};
+static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
                     const G1XYZZ& B1, const G2XYZZ& B2, const uint64_t r[4], const uint64_t s[4],
                     uint8_t proof_raw[256]) {
   if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) {
@@ -344,7 +351,8 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     memcpy(partial + 512, &q, 128);
     rc = FB_OK;
   } else {
-    rc = assemble(pk, H, L, A, B1, B2, r, s, proof_raw);
+    VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
+    rc = assemble(&vk, H, L, A, B1, B2, r, s, proof_raw);
   }
   auto t2 = std::chrono::steady_clock::now();
   collect_timings(std::chrono::duration<double, std::milli>(t2 - t1).count(),
@@ -483,6 +491,10 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
                (uint64_t)pk->len_b * (64 + 128 + 4) + info->nnz * 8 + 5 * pk->m * 32 +
                3 * (pk->m - 1) * 32 + (uint64_t)(pk->n_in + pk->n_aux) * 32;
   info->hbm_bytes = b;
+  info->g1_digit_slots = (uint64_t)pk->plan_h.n * pk->plan_h.W + (uint64_t)pk->plan_l.n * pk->plan_l.W +
+                         (uint64_t)pk->plan_a.n * pk->plan_a.W + (uint64_t)pk->plan_b.n * pk->plan_b.W;
+  info->g2_digit_slots = (uint64_t)pk->plan_b.n * pk->plan_b.W;
+  info->msm_window_bits = pk->plan_h.c;
   return FB_OK;
 }
 
@@ -512,10 +524,20 @@ int fb_prove_partial(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_
                     n_aux, nullptr, nullptr, nullptr, nullptr, partial, nullptr);
 }
 
-int fb_prove_finish(const fb_pk* pk_, const uint8_t* partials, int nparts, const uint64_t r[4],
-                    const uint64_t s[4], uint8_t proof_raw[256]) {
-  const ProvingKey* pk = reinterpret_cast<const ProvingKey*>(pk_);
-  if (!pk || !partials || nparts < 1 || !r || !s || !proof_raw) { set_error("fb_prove_finish: bad argument"); return FB_ERR_ARG; }
+int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* partials, int nparts,
+                    const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]) {
+  if (!bellman_params || !partials || nparts < 1 || !r || !s || !proof_raw) { set_error("fb_prove_finish: bad argument"); return FB_ERR_ARG; }
+  ParamsView v;
+  int rc = parse_params(bellman_params, len < 580 ? len : 580, v);
+  (void)rc;  // only the fixed-size verifying-key prefix is needed
+  if (len < 576) { set_error("Parameters truncated in verifying key"); return FB_ERR_FORMAT; }
+  VkPoints vk;
+  if (host_decode_g1(bellman_params, vk.alpha_g1) || host_decode_g1(bellman_params + 64, vk.beta_g1) ||
+      host_decode_g2(bellman_params + 128, vk.beta_g2) || host_decode_g1(bellman_params + 384, vk.delta_g1) ||
+      host_decode_g2(bellman_params + 448, vk.delta_g2)) {
+    set_error("invalid verifying-key point");
+    return FB_ERR_FORMAT;
+  }
   G1XYZZ sum[4] = {G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf()};
   G2XYZZ sum2 = G2XYZZ::inf();
   for (int i = 0; i < nparts; i++) {
@@ -529,7 +551,31 @@ int fb_prove_finish(const fb_pk* pk_, const uint8_t* partials, int nparts, const
     memcpy(&q, p + 512, 128);
     sum2 = add_mixed_cold(sum2, q);
   }
-  return assemble(pk, sum[0], sum[1], sum[2], sum[3], sum2, r, s, proof_raw);
+  return assemble(&vk, sum[0], sum[1], sum[2], sum[3], sum2, r, s, proof_raw);
+}
+
+int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const uint32_t** col,
+                   const uint32_t** cidx, uint64_t* nnz, const uint64_t** coef_table, uint64_t* ncoef) {
+  const Circuit* c = reinterpret_cast<const Circuit*>(c_);
+  if (!c || m < 0 || m > 2) return FB_ERR_ARG;
+  if (rowptr) *rowptr = c->csr.rowptr[m].data();
+  if (col) *col = c->csr.col[m].data();
+  if (cidx) *cidx = c->csr.cidx[m].data();
+  if (nnz) *nnz = c->csr.col[m].size();
+  if (coef_table) *coef_table = reinterpret_cast<const uint64_t*>(c->csr.coef.data());
+  if (ncoef) *ncoef = c->csr.coef.size();
+  return FB_OK;
+}
+
+uint64_t fb_launch_count(void) { return fb::g_launches; }
+void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
+void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
+int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {
+  if (which < 0 || which >= KSTAT_KINDS) return FB_ERR_ARG;
+  unsigned long long n = 0;
+  fb::kstat_collect(which, &n, total_ms);
+  if (launches) *launches = n;
+  return FB_OK;
 }
 
 int fb_prove_timings(const fb_pk* pk, float ms[6]) {

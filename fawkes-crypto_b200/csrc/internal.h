@@ -16,6 +16,13 @@
 namespace fb {
 
 void set_error(const char* fmt, ...);
+
+// ---- instrumentation (bench.py: gpu_launches and the live roofline timing) -------------
+extern unsigned long long g_launches;           // kernels launched by this library
+inline void count_launch(int n = 1) { g_launches += n; }
+enum { KSTAT_ACC_G1 = 0, KSTAT_ACC_G2 = 1, KSTAT_NTT = 2, KSTAT_KINDS = 3 };
+void kstat_begin(int kind, cudaStream_t st);    // no-ops unless enabled
+void kstat_end(int kind, cudaStream_t st);
 #define FB_CUDA(call)                                                              \
   do {                                                                             \
     cudaError_t _e = (call);                                                       \

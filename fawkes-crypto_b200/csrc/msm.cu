@@ -1,5 +1,6 @@
 // See msm.cuh for the design and the reference interface this replaces.
 #include "msm.cuh"
+#include "internal.h"
 
 #include <cstdlib>
 
@@ -22,21 +23,26 @@ MsmPlan MsmPlan::make(uint32_t n) {
   p.W = (255 + c - 1) / c;
   p.B = 1u << (c - 1);
   p.seg_log = c - 1 < 5 ? c - 1 : 5;
+  // task size: enough tasks to fill the chip, at most 256 adds per thread
+  uint64_t want = ((uint64_t)n * p.W) >> 18;
+  int tl = 4;
+  while (tl < 8 && (1ull << tl) < want) tl++;
+  if (tl < MSM_MIN_TASK_LOG) tl = MSM_MIN_TASK_LOG;
+  p.task_log = tl;
   return p;
 }
 
 int MsmScratch::alloc(uint64_t max_n, bool need_g2) {
   // worst case over all plans up to max_n: entries = n * W, buckets = W * B
-  uint64_t ent = 0, bk = 0;
-  for (uint64_t n = 1; n <= max_n; n = n * 2) {
-    uint64_t nn = n * 2 - 1 < max_n ? n * 2 - 1 : max_n;
+  uint64_t ent = 0, bk = 0, tk = 0;
+  auto consider = [&](uint64_t nn) {
     MsmPlan p = MsmPlan::make((uint32_t)nn);
     ent = std::max<uint64_t>(ent, (uint64_t)nn * p.W);
     bk = std::max<uint64_t>(bk, p.nbuckets());
-  }
-  MsmPlan p = MsmPlan::make((uint32_t)max_n);
-  ent = std::max<uint64_t>(ent, (uint64_t)max_n * p.W);
-  bk = std::max<uint64_t>(bk, p.nbuckets());
+    tk = std::max<uint64_t>(tk, (((uint64_t)nn * p.W) >> p.task_log) + p.nbuckets());
+  };
+  for (uint64_t n = 1; n <= max_n; n = n * 2) consider(n * 2 - 1 < max_n ? n * 2 - 1 : max_n);
+  consider(max_n);
   cap_entries = ent;
   cap_buckets = bk;
   size_t psz = need_g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);
@@ -49,12 +55,20 @@ int MsmScratch::alloc(uint64_t max_n, bool need_g2) {
   if (cudaMalloc(&segR, bk * psz) != cudaSuccess) return -1;  // nsegs <= nbuckets
   if (cudaMalloc(&segS, bk * psz) != cudaSuccess) return -1;
   if (cudaMalloc(&winsum, 256 * psz) != cudaSuccess) return -1;
+  // task decomposition of the bucket runs (load balancing under skewed digits)
+  cap_tasks = tk + 1;
+  if (cudaMalloc(&ntasks, (bk + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&task_off, (bk + 1) * 4) != cudaSuccess) return -1;
+  if (cudaMalloc(&partials, cap_tasks * psz) != cudaSuccess) return -1;
+  if (cudaMalloc(&heavy, (cap_tasks / MSM_HEAVY + 2) * 4) != cudaSuccess) return -1;
   return 0;
 }
 
 void MsmScratch::release() {
   cudaFree(hist); cudaFree(offsets); cudaFree(cursor); cudaFree(blocksums); cudaFree(sorted);
   cudaFree(buckets); cudaFree(segR); cudaFree(segS); cudaFree(winsum);
+  cudaFree(ntasks); cudaFree(task_off); cudaFree(partials); cudaFree(heavy);
+  ntasks = task_off = heavy = nullptr; partials = nullptr;
   hist = offsets = cursor = blocksums = sorted = nullptr;
   buckets = segR = segS = winsum = nullptr;
 }
@@ -163,34 +177,92 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
   if (i < n) {
     uint32_t v = out[i] + blocksums[blockIdx.x];
     out[i] = v;
-    cursor[i] = v;
+    if (cursor) cursor[i] = v;
   }
 }
 
 // ------------------------------------------------------------ accumulate ---
+// Bucket runs are cut into tasks of at most T = 2^task_log entries so that a bucket holding
+// a large share of the points (top window, witnesses full of 0/1) does not serialise.
+__global__ void k_task_count(const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
+                             uint32_t* __restrict__ ntasks) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nb) return;
+  if (b == nb) { ntasks[b] = 0; return; }
+  const uint32_t cnt = offsets[b + 1] - offsets[b];
+  ntasks[b] = (cnt + (1u << task_log) - 1) >> task_log;
+}
+
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ offsets, uint32_t nb, XYZZ<F>* __restrict__ buckets) {
+             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off,
+             uint32_t nb, int task_log, XYZZ<F>* __restrict__ partials) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= task_off[nb]) return;
+  // bucket b with task_off[b] <= t < task_off[b+1]
+  uint32_t lo = 0, hi = nb;  // invariant: task_off[lo] <= t < task_off[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (task_off[mid] <= t) lo = mid; else hi = mid;
+  }
+  const uint32_t b = lo;
+  const uint32_t start = offsets[b] + ((t - task_off[b]) << task_log);
+  const uint32_t end = min(start + (1u << task_log), offsets[b + 1]);
+  XYZZ<F> acc = XYZZ<F>::inf();
+  uint32_t e = sorted[start];
+  Affine<F> nxt = bases[e & 0x7fffffffu];
+  for (uint32_t p = start; p < end; p++) {
+    Affine<F> cur = nxt;
+    const uint32_t sign = e >> 31;
+    if (p + 1 < end) {
+      e = sorted[p + 1];
+      nxt = bases[e & 0x7fffffffu];
+    }
+    if (sign) cur.y = neg(cur.y);
+    acc = add_mixed(acc, cur);
+  }
+  partials[t] = acc;
+}
+
+// bucket = sum of its task partials; buckets with more than MSM_HEAVY partials are queued
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_gather(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ task_off,
+                uint32_t nb, XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const uint32_t start = offsets[b], end = offsets[b + 1];
-  XYZZ<F> acc = XYZZ<F>::inf();
-  if (start < end) {
-    uint32_t e = sorted[start];
-    Affine<F> nxt = bases[e & 0x7fffffffu];
-    for (uint32_t p = start; p < end; p++) {
-      Affine<F> cur = nxt;
-      const uint32_t sign = e >> 31;
-      if (p + 1 < end) {
-        e = sorted[p + 1];
-        nxt = bases[e & 0x7fffffffu];
-      }
-      if (sign) cur.y = neg(cur.y);
-      acc = add_mixed(acc, cur);
-    }
+  const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+  if (t1 - t0 > MSM_HEAVY) {
+    heavy[1 + atomicAdd(&heavy[0], 1u)] = b;
+    return;
   }
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t t = t0; t < t1; t++) acc = add_cold(acc, partials[t]);
   buckets[b] = acc;
+}
+
+// one CTA per queued bucket: strided partial sums then a shared-memory tree
+template <class F>
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS)
+k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ task_off,
+               const uint32_t* __restrict__ heavy, XYZZ<F>* __restrict__ buckets) {
+  __shared__ XYZZ<F> sh[MSM_HEAVY_THREADS];
+  const uint32_t count = heavy[0];
+  for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+    const uint32_t b = heavy[1 + i];
+    const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += MSM_HEAVY_THREADS) acc = add_cold(acc, partials[t]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = MSM_HEAVY_THREADS / 2; s > 0; s >>= 1) {
+      if ((int)threadIdx.x < s) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + s]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) buckets[b] = sh[0];
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------- reduce ---
@@ -304,7 +376,25 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
   XYZZ<F>* segS = reinterpret_cast<XYZZ<F>*>(s.segS);
   XYZZ<F>* winsum = reinterpret_cast<XYZZ<F>*>(s.winsum);
-  k_accumulate<F><<<(nb + 127) / 128, 128, 0, st>>>(bases, s.sorted, s.offsets, nb, buckets);
+  XYZZ<F>* partials = reinterpret_cast<XYZZ<F>*>(s.partials);
+  if (!reuse_sort) {
+    k_task_count<<<(nb + 1 + 255) / 256, 256, 0, st>>>(s.offsets, nb, p.task_log, s.ntasks);
+    const unsigned sb2 = (nb + 1 + 1023) / 1024;
+    k_scan_block<<<sb2, 1024, 0, st>>>(s.ntasks, s.task_off, s.blocksums, nb + 1);
+    k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb2);
+    k_scan_add<<<sb2, 1024, 0, st>>>(s.task_off, nullptr, s.blocksums, nb + 1);
+  }
+  const uint64_t max_tasks = (((uint64_t)p.n * p.W) >> p.task_log) + nb;
+  if (max_tasks > s.cap_tasks) return -4;
+  cudaMemsetAsync(s.heavy, 0, 4, st);
+  const int kind = sizeof(F) == sizeof(Fq) ? KSTAT_ACC_G1 : KSTAT_ACC_G2;
+  kstat_begin(kind, st);
+  k_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, s.task_off,
+                                                                     nb, p.task_log, partials);
+  kstat_end(kind, st);
+  count_launch(reuse_sort ? 7 : 16);
+  k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.task_off, nb, buckets, s.heavy);
+  k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.task_off, s.heavy, buckets);
   const uint32_t nsegs = p.nsegs();
   k_reduce_seg<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
   k_reduce_win<F><<<p.W, 32, 0, st>>>(segR, segS, p.B >> p.seg_log, p.seg_log, winsum);

@@ -12,8 +12,10 @@
 //                      bucket = window * 2^(c-1) + |d| - 1
 //   2. k_scan_*        exclusive prefix sum of the histogram (bucket offsets)
 //   3. k_scatter       counting-sort placement of (point index | sign << 31)
-//   4. k_accumulate    one thread per bucket, XYZZ mixed adds over its run, next base
-//                      prefetched while the current add executes
+//   4. k_accumulate    bucket runs cut into tasks of <= 2^task_log entries (a scan of the
+//                      per-bucket task counts maps task -> bucket); one thread per task,
+//                      XYZZ mixed adds, next base prefetched while the current add runs;
+//                      k_bucket_gather / k_bucket_heavy fold task partials into buckets
 //   5. k_reduce_*      sum_j (j+1) * B_j per window by segmented running sums
 //   6. k_combine       Horner over windows with c doublings between
 // Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
@@ -24,12 +26,18 @@
 
 namespace fb {
 
+constexpr int MSM_MIN_TASK_LOG = 4;
+constexpr uint32_t MSM_MIN_TASK = 1u << MSM_MIN_TASK_LOG;
+constexpr uint32_t MSM_HEAVY = 32;        // partials per bucket handled by one thread
+constexpr int MSM_HEAVY_THREADS = 128;
+
 struct MsmPlan {
   uint32_t n = 0;       // number of (scalar, base) pairs
   int c = 0;            // window bits
   int W = 0;            // number of windows, W*c >= 255
   uint32_t B = 0;       // buckets per window = 2^(c-1)
   int seg_log = 0;      // buckets per reduce segment = 2^seg_log
+  int task_log = 4;     // entries per accumulation task = 2^task_log
   static MsmPlan make(uint32_t n);
   uint32_t nbuckets() const { return (uint32_t)W * B; }
   uint32_t nsegs() const { return nbuckets() >> seg_log; }
@@ -46,7 +54,11 @@ struct MsmScratch {
   void* segR = nullptr;         // [nsegs] XYZZ
   void* segS = nullptr;         // [nsegs] XYZZ
   void* winsum = nullptr;       // [W] XYZZ
-  size_t cap_entries = 0, cap_buckets = 0;
+  uint32_t* ntasks = nullptr;   // [nbuckets + 1]
+  uint32_t* task_off = nullptr; // [nbuckets + 1]
+  void* partials = nullptr;     // [cap_tasks] XYZZ
+  uint32_t* heavy = nullptr;    // [0] = count, then bucket ids
+  size_t cap_entries = 0, cap_buckets = 0, cap_tasks = 0;
   int alloc(uint64_t max_n, bool need_g2);
   void release();
 };

@@ -22,6 +22,7 @@
 //  * The pointwise (a*b-c)/Z step is fused into the first pass of the final
 //    inverse transform.
 #include "ntt.cuh"
+#include "internal.h"
 
 #include <cstdio>
 
@@ -288,7 +289,10 @@ static void launch_pass(Fr* x, const Fr* y, const Fr* z, const Fr* t0, const Fr*
   int a = std::min(lb, NTT_LOG_TILE - b);
   size_t sm = (size_t)sizeof(Fr) << (a + b);
   unsigned blocks = 1u << (k - a - b);
+  kstat_begin(KSTAT_NTT, st);
   k_ntt_pass<MODE, NEG0><<<blocks, NTT_THREADS, sm, st>>>(x, y, z, t0, t1, k, lb, a, b, k1, k2);
+  kstat_end(KSTAT_NTT, st);
+  count_launch();
 }
 
 // x (natural order evaluations on H) -> natural order evaluations on gH, both scaled by m

@@ -29,6 +29,59 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error_cstr() { return g_err.c_str(); }
 
+unsigned long long g_launches = 0;
+namespace {
+struct KStat {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  struct Rec { int kind; cudaEvent_t a, b; };
+  std::vector<Rec> open_recs, recs;
+  unsigned long long count[KSTAT_KINDS] = {0, 0, 0};
+  double ms[KSTAT_KINDS] = {0, 0, 0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+} g_ks;
+}  // namespace
+void kstat_begin(int kind, cudaStream_t st) {
+  if (!g_ks.enabled) return;
+  KStat::Rec r{kind, g_ks.get(), g_ks.get()};
+  cudaEventRecord(r.a, st);
+  g_ks.open_recs.push_back(r);
+}
+void kstat_end(int kind, cudaStream_t st) {
+  if (!g_ks.enabled) return;
+  for (size_t i = g_ks.open_recs.size(); i-- > 0;) {
+    if (g_ks.open_recs[i].kind == kind) {
+      cudaEventRecord(g_ks.open_recs[i].b, st);
+      g_ks.recs.push_back(g_ks.open_recs[i]);
+      g_ks.open_recs.erase(g_ks.open_recs.begin() + i);
+      return;
+    }
+  }
+}
+void kstat_enable(bool on) { g_ks.enabled = on; }
+void kstat_reset() {
+  for (auto& r : g_ks.recs) { g_ks.pool.push_back(r.a); g_ks.pool.push_back(r.b); }
+  g_ks.recs.clear();
+  for (int i = 0; i < KSTAT_KINDS; i++) { g_ks.count[i] = 0; g_ks.ms[i] = 0; }
+}
+void kstat_collect(int kind, unsigned long long* launches, double* ms) {
+  cudaDeviceSynchronize();
+  for (auto& r : g_ks.recs) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { g_ks.count[r.kind]++; g_ks.ms[r.kind] += t; }
+    g_ks.pool.push_back(r.a);
+    g_ks.pool.push_back(r.b);
+  }
+  g_ks.recs.clear();
+  if (launches) *launches = g_ks.count[kind];
+  if (ms) *ms = g_ks.ms[kind];
+}
+
 // ---------------------------------------------------------------- brotli ---
 // libbrotlidec.so.1 ships without headers in this image: bind the three symbols we need.
 typedef struct BrotliDecoderStateStruct BrotliDecoderState;

@@ -46,6 +46,7 @@ int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c
     if (ng) {
       unsigned blocks = (unsigned)std::min<uint64_t>((ng + 127) / 128, 148 * 32);
       k_spmv<<<blocks, 128, 0, st>>>(csr.rowptr[i], csr.col[i], csr.cidx[i], csr.coef, w, outs[i], ng);
+      count_launch();
     }
   }
   // bellman appends `input_i * 0 = 0` for every input: a = w_i, b = c = 0

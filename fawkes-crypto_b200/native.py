@@ -29,7 +29,8 @@ class PkInfo(C.Structure):
     _fields_ = [("n_in", C.c_uint32), ("n_aux", C.c_uint32), ("n_gates", C.c_uint32),
                 ("log_m", C.c_uint32), ("len_h", C.c_uint32), ("len_l", C.c_uint32),
                 ("len_a", C.c_uint32), ("len_b", C.c_uint32), ("nnz", C.c_uint64),
-                ("hbm_bytes", C.c_uint64)]
+                ("hbm_bytes", C.c_uint64), ("g1_digit_slots", C.c_uint64), ("g2_digit_slots", C.c_uint64),
+                ("msm_window_bits", C.c_uint32)]
 
 
 # every symbol declared in include/fawkes_b200.h: (restype, argtypes)
@@ -51,13 +52,18 @@ SIGNATURES = {
     "fb_prove": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp]),
     "fb_prove_device": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "fb_prove_partial": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp]),
-    "fb_prove_finish": (C.c_int, [vp, vp, C.c_int, vp, vp, vp]),
+    "fb_prove_finish": (C.c_int, [vp, C.c_size_t, vp, C.c_int, vp, vp, vp]),
     "fb_prove_timings": (C.c_int, [vp, f32p]),
     "fb_setup": (C.c_int, [vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "fb_verify": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(C.c_int)]),
     "fb_circuit_synth": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "fb_circuit_witness": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
     "fb_synth_trapdoor": (C.c_int, [C.c_uint64, vp]),
+    "fb_circuit_csr": (C.c_int, [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(C.c_uint64)]),
+    "fb_launch_count": (C.c_uint64, []),
+    "fb_kernel_stats_enable": (None, [C.c_int]),
+    "fb_kernel_stats_reset": (None, []),
+    "fb_kernel_stats": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "fb_test_field": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_uint64]),
     "fb_test_ntt": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_test_h": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, f32p]),

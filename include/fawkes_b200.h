@@ -67,6 +67,9 @@ typedef struct fb_pk_info {
   uint32_t len_h, len_l, len_a, len_b;
   uint64_t nnz;       /* total non-zeros of A,B,C */
   uint64_t hbm_bytes; /* device memory held by the key */
+  uint64_t g1_digit_slots; /* sum over the four G1 MSMs of n x windows = mixed adds per prove (upper bound) */
+  uint64_t g2_digit_slots;
+  uint32_t msm_window_bits; /* window size chosen for the H MSM */
 } fb_pk_info;
 
 /* ---- context --------------------------------------------------------------- */
@@ -113,8 +116,8 @@ int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[
  * 128 B) and b_g2 (128 B): 5 x 128 B.  Combine with fb_prove_finish on any rank. */
 int fb_prove_partial(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in,
                      const uint64_t* aux, uint32_t n_aux, uint8_t partial[640]);
-int fb_prove_finish(const fb_pk* pk, const uint8_t* partials, int nparts, const uint64_t r[4],
-                    const uint64_t s[4], uint8_t proof_raw[256]);
+int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* partials, int nparts,
+                    const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]); /* host only */
 /* device-time breakdown of the last fb_prove on this key, milliseconds:
  * [0] h2d  [1] r1cs eval  [2] H pipeline (7 NTTs)  [3] MSMs  [4] d2h+assembly (host)  [5] total */
 int fb_prove_timings(const fb_pk* pk, float ms[6]);
@@ -134,6 +137,17 @@ int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t proof_raw[256]
 int fb_circuit_synth(uint64_t n_rows, uint64_t seed, fb_circuit** out);
 int fb_circuit_witness(const fb_circuit* c, const uint64_t** inputs, const uint64_t** aux);
 int fb_synth_trapdoor(uint64_t seed, uint64_t out[7][4]); /* alpha beta gamma delta tau r s */
+/* borrowed views of matrix m (0 A, 1 B, 2 C) in CSR over w = [inputs | aux]; cidx 0 -> ONE,
+ * 1 -> -ONE, k >= 2 -> coef_table[k-2] (Montgomery) */
+int fb_circuit_csr(const fb_circuit* c, int m, const uint32_t** rowptr, const uint32_t** col,
+                   const uint32_t** cidx, uint64_t* nnz, const uint64_t** coef_table, uint64_t* ncoef);
+/* instrumentation: kernels launched by the library so far; CUDA-event timing of the dominant
+ * kernels on their launching stream (which: 0 G1 bucket accumulation, 1 G2 bucket
+ * accumulation, 2 NTT passes) */
+uint64_t fb_launch_count(void);
+void fb_kernel_stats_enable(int on);
+void fb_kernel_stats_reset(void);
+int fb_kernel_stats(int which, uint64_t* launches, double* total_ms);
 /* op: 0 mul 1 add 2 sub 3 inv 4 portable-C mul; field: 0 Fr 1 Fq; host buffers [n][4] */
 int fb_test_field(fb_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b,
                   uint64_t* out, uint64_t n);
