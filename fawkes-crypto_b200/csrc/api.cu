@@ -197,9 +197,8 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   pk->plan_l = MsmPlan::make((uint32_t)l_cnt);
   pk->plan_a = MsmPlan::make(pk->len_a);
   pk->plan_b = MsmPlan::make(pk->len_b);
-  uint64_t maxn = std::max<uint64_t>(std::max<uint64_t>(pk->len_h, l_cnt),
-                                     std::max<uint64_t>(pk->len_a, pk->len_b));
-  if (pk->msm.alloc(std::max<uint64_t>(maxn, 1), true) != 0) {
+  const uint64_t msm_sizes[4] = {pk->len_h, l_cnt, pk->len_a, pk->len_b};
+  if (pk->msm.alloc(msm_sizes, 4, true) != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
     return FB_ERR_CUDA;

@@ -32,17 +32,16 @@ MsmPlan MsmPlan::make(uint32_t n) {
   return p;
 }
 
-int MsmScratch::alloc(uint64_t max_n, bool need_g2) {
-  // worst case over all plans up to max_n: entries = n * W, buckets = W * B
-  uint64_t ent = 0, bk = 0, tk = 0;
-  auto consider = [&](uint64_t nn) {
-    MsmPlan p = MsmPlan::make((uint32_t)nn);
-    ent = std::max<uint64_t>(ent, (uint64_t)nn * p.W);
+int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
+  // capacity = max over the plans that will actually run on this scratch
+  uint64_t ent = 1, bk = 1, tk = 1;
+  for (int i = 0; i < count; i++) {
+    if (sizes[i] == 0) continue;
+    MsmPlan p = MsmPlan::make((uint32_t)sizes[i]);
+    ent = std::max<uint64_t>(ent, sizes[i] * p.W);
     bk = std::max<uint64_t>(bk, p.nbuckets());
-    tk = std::max<uint64_t>(tk, (((uint64_t)nn * p.W) >> p.task_log) + p.nbuckets());
-  };
-  for (uint64_t n = 1; n <= max_n; n = n * 2) consider(n * 2 - 1 < max_n ? n * 2 - 1 : max_n);
-  consider(max_n);
+    tk = std::max<uint64_t>(tk, ((sizes[i] * p.W) >> p.task_log) + p.nbuckets());
+  }
   cap_entries = ent;
   cap_buckets = bk;
   size_t psz = need_g2 ? sizeof(G2XYZZ) : sizeof(G1XYZZ);

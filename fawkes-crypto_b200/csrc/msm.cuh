@@ -59,7 +59,7 @@ struct MsmScratch {
   void* partials = nullptr;     // [cap_tasks] XYZZ
   uint32_t* heavy = nullptr;    // [0] = count, then bucket ids
   size_t cap_entries = 0, cap_buckets = 0, cap_tasks = 0;
-  int alloc(uint64_t max_n, bool need_g2);
+  int alloc(const uint64_t* sizes, int count, bool need_g2);
   void release();
 };
 

@@ -175,7 +175,7 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   FB_CUDA(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, st));
   MsmPlan plan = MsmPlan::make((uint32_t)n);
   MsmScratch scr;
-  if (scr.alloc(n, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
+  if (scr.alloc(&n, 1, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
