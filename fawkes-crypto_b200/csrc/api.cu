@@ -63,7 +63,7 @@ static void pk_release(ProvingKey* pk) {
   cudaFree(pk->w);
   for (int i = 0; i < 3; i++) cudaFree(pk->ev[i]);
   cudaFree(pk->scratch);
-  pk->msm.release();
+  for (auto& x : pk->msm) x.release();
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
   delete pk;
@@ -198,13 +198,15 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   pk->plan_a = MsmPlan::make(pk->len_a);
   pk->plan_b = MsmPlan::make(pk->len_b);
   const uint64_t msm_sizes[4] = {pk->len_h, l_cnt, pk->len_a, pk->len_b};
-  if (pk->msm.alloc(msm_sizes, 4, true) != 0) {
+  int arc = 0;
+  for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_sizes[i], 1, i == 3);
+  if (arc != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
     return FB_ERR_CUDA;
   }
-  PK_CUDA(cudaMalloc(&pk->results, 5 * sizeof(G2XYZZ)));
-  PK_CUDA(cudaMallocHost(&pk->results_host, 5 * sizeof(G2XYZZ)));
+  PK_CUDA(cudaMalloc(&pk->results, 7 * sizeof(G2XYZZ)));
+  PK_CUDA(cudaMallocHost(&pk->results_host, 7 * sizeof(G2XYZZ)));
   PK_CUDA(cudaStreamSynchronize(st));
   *out = pk;
   return FB_OK;
@@ -226,16 +228,20 @@ struct VkPoints {
   G1Affine alpha_g1, beta_g1, delta_g1;
   G2Affine beta_g2, delta_g2;
 };
-static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
-                    const G1XYZZ& B1, const G2XYZZ& B2, const uint64_t r[4], const uint64_t s[4],
-                    uint8_t proof_raw[256]) {
+struct FixedTerms {  // the parts of A, B, C that depend on r, s and the key only
+  G1XYZZ a;   // alpha + r*delta
+  G2XYZZ b;   // beta2 + s*delta2
+  G1XYZZ c;   // rs*delta + s*alpha + r*beta1
+  uint32_t rc[8], sc[8];
+};
+static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s[4], FixedTerms& f) {
   if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) {
     set_error("UnexpectedIdentity: delta is the point at infinity");
     return FB_ERR_IDENTITY;
   }
-  uint32_t rc[8], sc[8], rsc[8];
-  fr_canonical(r, rc);
-  fr_canonical(s, sc);
+  uint32_t rsc[8];
+  fr_canonical(r, f.rc);
+  fr_canonical(s, f.sc);
   Fr rm, sm;
   memcpy(rm.v, r, 32);
   memcpy(sm.v, s, 32);
@@ -244,13 +250,21 @@ static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const 
   G1XYZZ d1 = G1XYZZ::from_affine(pk->delta_g1), al = G1XYZZ::from_affine(pk->alpha_g1),
          be1 = G1XYZZ::from_affine(pk->beta_g1);
   G2XYZZ d2 = G2XYZZ::from_affine(pk->delta_g2);
-  G1XYZZ g_a = add_cold(add_mixed_cold(scalar_mul(d1, rc), pk->alpha_g1), A);
-  G2XYZZ g_b = add_cold(add_mixed_cold(scalar_mul(d2, sc), pk->beta_g2), B2);
-  G1XYZZ g_c = scalar_mul(d1, rsc);
-  g_c = add_cold(g_c, scalar_mul(al, sc));
-  g_c = add_cold(g_c, scalar_mul(be1, rc));
-  g_c = add_cold(g_c, scalar_mul(A, sc));
-  g_c = add_cold(g_c, scalar_mul(B1, rc));
+  f.a = add_mixed_cold(scalar_mul(d1, f.rc), pk->alpha_g1);
+  f.b = add_mixed_cold(scalar_mul(d2, f.sc), pk->beta_g2);
+  f.c = scalar_mul(d1, rsc);
+  f.c = add_cold(f.c, scalar_mul(al, f.sc));
+  f.c = add_cold(f.c, scalar_mul(be1, f.rc));
+  return FB_OK;
+}
+// sA = s*sum_a and rB1 = r*sum_b1 come from the device when available (null -> host)
+static void finish_proof(const FixedTerms& f, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
+                         const G1XYZZ& B1, const G2XYZZ& B2, const G1XYZZ* sA, const G1XYZZ* rB1,
+                         uint8_t proof_raw[256]) {
+  G1XYZZ g_a = add_cold(f.a, A);
+  G2XYZZ g_b = add_cold(f.b, B2);
+  G1XYZZ g_c = add_cold(f.c, sA ? *sA : scalar_mul(A, f.sc));
+  g_c = add_cold(g_c, rB1 ? *rB1 : scalar_mul(B1, f.rc));
   g_c = add_cold(g_c, H);
   g_c = add_cold(g_c, L);
   G1Affine pa = to_affine(g_a), pc = to_affine(g_c);
@@ -258,21 +272,55 @@ static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const 
   memcpy(proof_raw, &pa, 64);
   memcpy(proof_raw + 64, &pb, 128);
   memcpy(proof_raw + 192, &pc, 64);
+}
+static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
+                    const G1XYZZ& B1, const G2XYZZ& B2, const uint64_t r[4], const uint64_t s[4],
+                    uint8_t proof_raw[256]) {
+  FixedTerms f;
+  int rc = fixed_terms(pk, r, s, f);
+  if (rc) return rc;
+  finish_proof(f, H, L, A, B1, B2, nullptr, nullptr, proof_raw);
   return FB_OK;
 }
 
-// device part: w already in pk->w.  Leaves five XYZZ sums in pk->results_host.
-static int prove_device_part(ProvingKey* pk, uint64_t* h_out) {
-  cudaStream_t st = pk->ctx->stream;
+static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
+
+// device part: w already in pk->w (on the main stream).  Leaves the five XYZZ sums (+ s*A, r*B1
+// when r, s are given) in pk->results_host.  NOT synchronised on return.
+static int prove_launch(ProvingKey* pk, uint64_t* h_out, const uint64_t* r, const uint64_t* s) {
+  Ctx* ctx = pk->ctx;
+  cudaStream_t st = ctx->stream;
+  cudaStream_t sL = g_serial ? st : ctx->aux[0], sA = g_serial ? st : ctx->aux[1],
+               sB = g_serial ? st : ctx->aux[2];
   Timing& T = g_timing;
-  if (!T.init) {
-    for (auto& e : T.ev) cudaEventCreate(&e);
-    T.init = true;
-  }
   const uint64_t m = pk->m;
-  cudaEventRecord(T.ev[1], st);
-  int rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
-  if (rc) return rc;
+  G2XYZZ* res = reinterpret_cast<G2XYZZ*>(pk->results);
+  FB_CUDA(cudaMemsetAsync(res, 0, 7 * sizeof(G2XYZZ), st));
+  cudaEventRecord(T.ev[1], st);  // witness resident
+  if (!g_serial) {
+    for (int i = 0; i < 3; i++) FB_CUDA(cudaStreamWaitEvent(ctx->aux[i], T.ev[1], 0));
+  }
+  const uint64_t nh = m - 1;
+  const uint64_t h_lo = nh * pk->shard / pk->nshards;
+  const uint64_t l_lo = (uint64_t)pk->n_aux * pk->shard / pk->nshards;
+  // witness-only MSMs start at once on their own streams; the G2 one first (longest tail)
+  int rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm[3], res + 4, false, sB);
+  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm[3], (G1XYZZ*)(res + 3), true, sB);
+  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm[2], (G1XYZZ*)(res + 2), false, sA);
+  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)(res + 1), false, sL);
+  if (r && s) {
+    Fr rm, sm;
+    memcpy(rm.v, r, 32);
+    memcpy(sm.v, s, 32);
+    scalar_mul_g1((const G1XYZZ*)(res + 2), sm, pk->msm[2], (G1XYZZ*)(res + 5), sA);
+    scalar_mul_g1((const G1XYZZ*)(res + 3), rm, pk->msm[3], (G1XYZZ*)(res + 6), sB);
+  }
+  // R1CS evaluation and the H pipeline on the main stream
+  if (!rc) rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
+  if (rc > 0 || rc < 0) {
+    if (rc != FB_ERR_CUDA) set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    return FB_ERR_CUDA;
+  }
   cudaEventRecord(T.ev[2], st);
   for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(pk->ev[i], st);
   pk->dom.pointwise_then_icoset_fft(pk->ev[0], pk->ev[1], pk->ev[2], st);
@@ -281,21 +329,16 @@ static int prove_device_part(ProvingKey* pk, uint64_t* h_out) {
     pk->dom.bitrev(pk->scratch, pk->ev[0], st);
     FB_CUDA(cudaMemcpyAsync(h_out, pk->scratch, (m - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
   }
-  G2XYZZ* res = reinterpret_cast<G2XYZZ*>(pk->results);
-  FB_CUDA(cudaMemsetAsync(res, 0, 5 * sizeof(G2XYZZ), st));
-  const uint64_t nh = m - 1;
-  const uint64_t h_lo = nh * pk->shard / pk->nshards;
-  const uint64_t l_lo = (uint64_t)pk->n_aux * pk->shard / pk->nshards;
-  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm, (G1XYZZ*)(res + 0), false, st);
-  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm, (G1XYZZ*)(res + 1), false, st);
-  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm, (G1XYZZ*)(res + 2), false, st);
-  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm, (G1XYZZ*)(res + 3), false, st);
-  if (!rc) rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm, res + 4, true, st);
+  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm[0], (G1XYZZ*)(res + 0), false, st);
   if (rc) { set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
+  if (!g_serial) {
+    for (int i = 0; i < 3; i++) {
+      FB_CUDA(cudaEventRecord(ctx->aux_done[i], ctx->aux[i]));
+      FB_CUDA(cudaStreamWaitEvent(st, ctx->aux_done[i], 0));
+    }
+  }
   cudaEventRecord(T.ev[4], st);
-  FB_CUDA(cudaMemcpyAsync(pk->results_host, res, 5 * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
-  FB_CUDA(cudaStreamSynchronize(st));
-  FB_CUDA(cudaGetLastError());
+  FB_CUDA(cudaMemcpyAsync(pk->results_host, res, 7 * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
   return FB_OK;
 }
 
@@ -332,12 +375,19 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));
   }
-  int rc = prove_device_part(pk, h_out);
-  if (rc) return rc;
+  int rc = prove_launch(pk, h_out, partial ? nullptr : r, partial ? nullptr : s);
+  if (rc) { cudaStreamSynchronize(st); return rc; }
+  // host work that needs only r, s and the key overlaps the device
+  FixedTerms ft;
+  VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
+  int rc_fixed = partial ? FB_OK : fixed_terms(&vk, r, s, ft);
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
+  if (rc_fixed) return rc_fixed;
   auto t1 = std::chrono::steady_clock::now();
   const G2XYZZ* res = reinterpret_cast<const G2XYZZ*>(pk->results_host);
   G1XYZZ H = *(const G1XYZZ*)(res + 0), L = *(const G1XYZZ*)(res + 1), A = *(const G1XYZZ*)(res + 2),
-         B1 = *(const G1XYZZ*)(res + 3);
+         B1 = *(const G1XYZZ*)(res + 3), sA = *(const G1XYZZ*)(res + 5), rB1 = *(const G1XYZZ*)(res + 6);
   G2XYZZ B2 = res[4];
   if (partial) {
     memset(partial, 0, 640);
@@ -350,8 +400,8 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     memcpy(partial + 512, &q, 128);
     rc = FB_OK;
   } else {
-    VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
-    rc = assemble(&vk, H, L, A, B1, B2, r, s, proof_raw);
+    finish_proof(ft, H, L, A, B1, B2, &sA, &rB1, proof_raw);
+    rc = FB_OK;
   }
   auto t2 = std::chrono::steady_clock::now();
   collect_timings(std::chrono::duration<double, std::milli>(t2 - t1).count(),
@@ -391,6 +441,10 @@ int fb_init(const int* devices, int ndev, fb_ctx** out) {
   Ctx* c = new Ctx();
   c->device = dev;
   FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 3; i++) {
+    FB_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    FB_CUDA(cudaEventCreateWithFlags(&c->aux_done[i], cudaEventDisableTiming));
+  }
   *out = reinterpret_cast<fb_ctx*>(c);
   return FB_OK;
 }
@@ -400,6 +454,7 @@ void fb_shutdown(fb_ctx* ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 3; i++) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
   delete c;
 }
 
@@ -567,6 +622,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
 }
 
 uint64_t fb_launch_count(void) { return fb::g_launches; }
+void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {

@@ -52,7 +52,9 @@ struct DevCsr {
 
 struct Ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // R1CS eval, H pipeline, H MSM, copies
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // L / A / B MSMs run beside the H pipeline
+  cudaEvent_t aux_done[3] = {nullptr, nullptr, nullptr};
 };
 
 struct ProvingKey {
@@ -78,9 +80,9 @@ struct ProvingKey {
   Fr* w = nullptr;         // n_in + n_aux
   Fr* ev[3] = {nullptr, nullptr, nullptr};  // m each
   Fr* scratch = nullptr;   // m (h_out permutation)
-  MsmScratch msm;
+  MsmScratch msm[4];       // H, L, A, B (B_g1 and B_g2 share one sort)
   MsmPlan plan_h, plan_l, plan_a, plan_b;
-  void* results = nullptr;       // 5 x G2XYZZ slots on device
+  void* results = nullptr;       // 7 x G2XYZZ slots on device: H L A B1 B2 s*A r*B1
   void* results_host = nullptr;  // pinned
   // base-index shard handled by this key (multi-GPU): fractions [shard, shard+1)/nshards
   int shard = 0, nshards = 1;

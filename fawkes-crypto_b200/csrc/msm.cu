@@ -51,8 +51,8 @@ int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
   if (cudaMalloc(&blocksums, ((bk + 1023) / 1024 + 1) * 4) != cudaSuccess) return -1;
   if (cudaMalloc(&sorted, std::max<uint64_t>(ent, 1) * 4) != cudaSuccess) return -1;
   if (cudaMalloc(&buckets, bk * psz) != cudaSuccess) return -1;
-  if (cudaMalloc(&segR, bk * psz) != cudaSuccess) return -1;  // nsegs <= nbuckets
-  if (cudaMalloc(&segS, bk * psz) != cudaSuccess) return -1;
+  if (cudaMalloc(&segR, 512 * psz) != cudaSuccess) return -1;  // U[p], p < W*c
+  if (cudaMalloc(&segS, 512 * psz) != cudaSuccess) return -1;  // tree scratch of k_pow2_sum
   if (cudaMalloc(&winsum, 256 * psz) != cudaSuccess) return -1;
   // task decomposition of the bucket runs (load balancing under skewed digits)
   cap_tasks = tk + 1;
@@ -265,88 +265,63 @@ k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------- reduce ---
-// per segment of K = 2^seg_log buckets:  R = sum (t+1) * B_t,  S = sum B_t
-template <class F>
-__global__ void __launch_bounds__(128)
-k_reduce_seg(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, int seg_log,
-             XYZZ<F>* __restrict__ segR, XYZZ<F>* __restrict__ segS) {
-  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsegs) return;
-  const uint32_t K = 1u << seg_log;
-  const XYZZ<F>* bk = buckets + ((uint64_t)s << seg_log);
-  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
-  for (int t = (int)K - 1; t >= 0; t--) {
-    run = add_cold(run, bk[t]);
-    tot = add_cold(tot, run);
-  }
-  segR[s] = tot;
-  segS[s] = run;
-}
-
-// one warp per window: winsum = sum_s R_s + K * sum_s s * S_s
-template <class F>
-__global__ void __launch_bounds__(32)
-k_reduce_win(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ segS, uint32_t segs,
-             int seg_log, XYZZ<F>* __restrict__ winsum) {
-  __shared__ XYZZ<F> shR[32], shW[32], shS[32];
-  const uint32_t w = blockIdx.x, lane = threadIdx.x;
-  const XYZZ<F>* R = segR + (uint64_t)w * segs;
-  const XYZZ<F>* S = segS + (uint64_t)w * segs;
-  // lane handles segments [lo, hi); chunk = ceil(segs / 32)
-  const uint32_t chunk = (segs + 31) / 32;
-  const uint32_t lo = lane * chunk, hi = min(segs, lo + chunk);
-  XYZZ<F> sumR = XYZZ<F>::inf(), run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
-  for (int s = (int)hi - 1; s >= (int)lo; s--) {
-    sumR = add_cold(sumR, R[s]);
-    run = add_cold(run, S[s]);
-    tot = add_cold(tot, run);  // sum (s - lo + 1) * S_s
-  }
-  shR[lane] = sumR;  // sum of R
-  shW[lane] = tot;   // local weighted (weights 1..)
-  shS[lane] = run;   // plain sum of S
-  __syncwarp();
-  if (lane == 0) {
-    // sum_s s*S_s = sum_lanes [ (W_lane - S_lane) + lo_lane * S_lane ],  lo_lane = lane*chunk
-    XYZZ<F> accR = XYZZ<F>::inf(), accW = XYZZ<F>::inf(), accS = XYZZ<F>::inf();
-    XYZZ<F> run2 = XYZZ<F>::inf(), tot2 = XYZZ<F>::inf();  // sum lane * S_lane via running sum
-    for (int l = 31; l >= 0; l--) {
-      accR = add_cold(accR, shR[l]);
-      accW = add_cold(accW, shW[l]);
-      accS = add_cold(accS, shS[l]);
-      if (l >= 1) {
-        run2 = add_cold(run2, shS[l]);
-        tot2 = add_cold(tot2, run2);
-      }
+// sum_w 2^(c w) sum_j (j+1) B[w][j]  is evaluated bit-wise: with p = c w + k,
+//   U[p] = sum of the buckets of window w whose value (j+1) has bit k set      (plain sums)
+//   result = sum_p 2^p U[p]
+// k_bucket_bits: one CTA per p, strided partial sums + shared-memory tree (no serial running sum).
+// k_pow2_sum:    thread p doubles its term p times, then a tree over the W*c terms; the depth is
+//                the unavoidable ~255 doublings, everything else is parallel.
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_bucket_bits(const XYZZ<F>* __restrict__ buckets, int c, uint32_t B, XYZZ<F>* __restrict__ U) {
+  __shared__ XYZZ<F> sh[THREADS];
+  const int p = blockIdx.x, w = p / c, k = p % c;
+  const XYZZ<F>* bk = buckets + (uint64_t)w * B;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  // values v = j+1 in [1, B] with bit k set: enumerate t in [0, B/2] -> v
+  if (k == c - 1) {
+    if (threadIdx.x == 0) acc = bk[B - 1];  // only v = B = 2^(c-1) has bit c-1
+  } else {
+    const uint32_t low_mask = (1u << k) - 1;
+    for (uint32_t t = threadIdx.x; t < (B >> 1); t += THREADS) {
+      // insert a 1 at bit position k of t
+      const uint32_t v = ((t & ~low_mask) << 1) | (1u << k) | (t & low_mask);
+      if (v <= B) acc = add_cold(acc, bk[v - 1]);
     }
-    // chunk * tot2 by double-and-add on the small integer chunk
-    XYZZ<F> ct = XYZZ<F>::inf();
-    for (int bit = 31; bit >= 0; bit--) {
-      ct = dbl_cold(ct);
-      if ((chunk >> bit) & 1) ct = add_cold(ct, tot2);
-    }
-    XYZZ<F> T = add_cold(add_cold(accW, neg(accS)), ct);  // sum_s s * S_s
-    for (int i = 0; i < seg_log; i++) T = dbl_cold(T);
-    winsum[w] = add_cold(accR, T);
   }
-}
-
-// result = sum_w 2^(c w) * winsum[w]
-template <class F>
-__global__ void __launch_bounds__(64)
-k_combine(const XYZZ<F>* __restrict__ winsum, int W, int c, XYZZ<F>* __restrict__ out) {
-  __shared__ XYZZ<F> sh[64];
-  const int w = threadIdx.x;
-  if (w < W) {
-    XYZZ<F> x = winsum[w];
-    for (int i = 0; i < w * c; i++) x = dbl_cold(x);
-    sh[w] = x;
-  }
+  sh[threadIdx.x] = acc;
   __syncthreads();
-  if (w == 0) {
-    XYZZ<F> acc = sh[0];
-    for (int i = 1; i < W; i++) acc = add_cold(acc, sh[i]);
-    *out = acc;
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
   }
+  if (threadIdx.x == 0) U[p] = sh[0];
+}
+
+// out = sum_{p < n} 2^p V[p]  (n <= 512).  SCALAR: V[p] = bit p of k ? *one : infinity.
+template <class F, bool SCALAR>
+__global__ void __launch_bounds__(512)
+k_pow2_sum(const XYZZ<F>* __restrict__ V, int n, Fr k_mont, XYZZ<F>* __restrict__ tmp,
+           XYZZ<F>* __restrict__ out) {
+  const int p = threadIdx.x;
+  XYZZ<F> x = XYZZ<F>::inf();
+  if (p < n) {
+    if (SCALAR) {
+      Fr k = from_mont(k_mont);
+      if (p < 256 && ((k.v[p >> 5] >> (p & 31)) & 1)) x = V[0];
+    } else {
+      x = V[p];
+    }
+    if (!x.is_inf())
+      for (int i = 0; i < p; i++) x = dbl_cold(x);
+  }
+  tmp[p] = x;
+  __syncthreads();
+  for (int s = 256; s > 0; s >>= 1) {
+    if (p < s) tmp[p] = add_cold(tmp[p], tmp[p + s]);
+    __syncthreads();
+  }
+  if (p == 0) *out = tmp[0];
 }
 
 // ----------------------------------------------------------------- driver ---
@@ -374,7 +349,6 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(s.buckets);
   XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
   XYZZ<F>* segS = reinterpret_cast<XYZZ<F>*>(s.segS);
-  XYZZ<F>* winsum = reinterpret_cast<XYZZ<F>*>(s.winsum);
   XYZZ<F>* partials = reinterpret_cast<XYZZ<F>*>(s.partials);
   if (!reuse_sort) {
     k_task_count<<<(nb + 1 + 255) / 256, 256, 0, st>>>(s.offsets, nb, p.task_log, s.ntasks);
@@ -391,13 +365,19 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   k_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, s.task_off,
                                                                      nb, p.task_log, partials);
   kstat_end(kind, st);
-  count_launch(reuse_sort ? 7 : 16);
+  count_launch(reuse_sort ? 5 : 14);
   k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.task_off, nb, buckets, s.heavy);
   k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.task_off, s.heavy, buckets);
-  const uint32_t nsegs = p.nsegs();
-  k_reduce_seg<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
-  k_reduce_win<F><<<p.W, 32, 0, st>>>(segR, segS, p.B >> p.seg_log, p.seg_log, winsum);
-  k_combine<F><<<1, 64, 0, st>>>(winsum, p.W, p.c, out);
+  const int nbits = p.W * p.c;  // <= 255 + c - 1 < 512
+  constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
+  k_bucket_bits<F, BT><<<nbits, BT, 0, st>>>(buckets, p.c, p.B, segR);
+  k_pow2_sum<F, false><<<1, 512, 0, st>>>(segR, nbits, Fr::zero(), segS, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st) {
+  k_pow2_sum<Fq, true><<<1, 512, 0, st>>>(point, 256, k_mont, reinterpret_cast<G1XYZZ*>(s.segS), out);
+  count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -16,8 +16,8 @@
 //                      per-bucket task counts maps task -> bucket); one thread per task,
 //                      XYZZ mixed adds, next base prefetched while the current add runs;
 //                      k_bucket_gather / k_bucket_heavy fold task partials into buckets
-//   5. k_reduce_*      sum_j (j+1) * B_j per window by segmented running sums
-//   6. k_combine       Horner over windows with c doublings between
+//   5. k_bucket_bits   U[p] = sum of the buckets whose value has bit (p mod c) set, window p / c
+//   6. k_pow2_sum      sum_p 2^p U[p]: thread p doubles p times, then a tree
 // Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
 #pragma once
 #include <cuda_runtime.h>
@@ -51,8 +51,8 @@ struct MsmScratch {
   uint32_t* blocksums = nullptr;
   uint32_t* sorted = nullptr;   // [n * W]
   void* buckets = nullptr;      // [nbuckets] XYZZ (sized for G2)
-  void* segR = nullptr;         // [nsegs] XYZZ
-  void* segS = nullptr;         // [nsegs] XYZZ
+  void* segR = nullptr;         // [512] XYZZ: per-bit sums U[p]
+  void* segS = nullptr;         // [512] XYZZ: tree scratch
   void* winsum = nullptr;       // [W] XYZZ
   uint32_t* ntasks = nullptr;   // [nbuckets + 1]
   uint32_t* task_off = nullptr; // [nbuckets + 1]
@@ -68,6 +68,8 @@ struct MsmScratch {
 // (same scalars as the previous call on this scratch: B_g1 then B_g2).
 int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
            MsmScratch& s, G1XYZZ* out, bool reuse_sort, cudaStream_t st);
+// out = k * point (one point), same parallel doubling tree; uses s.segS as scratch
+int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st);
 int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
            MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st);
 

@@ -145,6 +145,9 @@ int fb_circuit_csr(const fb_circuit* c, int m, const uint32_t** rowptr, const ui
  * kernels on their launching stream (which: 0 G1 bucket accumulation, 1 G2 bucket
  * accumulation, 2 NTT passes) */
 uint64_t fb_launch_count(void);
+/* 1: run every kernel of a prove on one stream (per-kernel timings are then undisturbed);
+ * 0 (default): the witness-only MSMs run on side streams beside the H pipeline */
+void fb_set_serial(int on);
 void fb_kernel_stats_enable(int on);
 void fb_kernel_stats_reset(void);
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms);
