@@ -229,7 +229,7 @@ def run_ours(args):
             dist.all_gather_into_tensor(gathered, mine)
             if rank == 0:
                 parts = gathered.cpu().numpy()
-                fb.native.check(lib.fb_prove_finish(fb.native.ptr(params.bellman_bytes), len(params.bellman_bytes),
+                fb.native.check(lib.fb_prove_finish(fb.native.ptr(params.bellman_bytes), 580,
                                                     parts.ctypes.data, world, r.ctypes.data, s.ctypes.data,
                                                     proof.ctypes.data))
 

@@ -298,9 +298,10 @@ k_bucket_bits(const XYZZ<F>* __restrict__ buckets, int c, uint32_t B, XYZZ<F>* _
   if (threadIdx.x == 0) U[p] = sh[0];
 }
 
-// out = sum_{p < n} 2^p V[p]  (n <= 512).  SCALAR: V[p] = bit p of k ? *one : infinity.
+constexpr int POW2_THREADS = 288;  // >= W*c for every plan (255 + c - 1 <= 278)
+// out = sum_{p < n} 2^p V[p]  (n <= POW2_THREADS).  SCALAR: V[p] = bit p of k ? *one : infinity.
 template <class F, bool SCALAR>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(POW2_THREADS)
 k_pow2_sum(const XYZZ<F>* __restrict__ V, int n, Fr k_mont, XYZZ<F>* __restrict__ tmp,
            XYZZ<F>* __restrict__ out) {
   const int p = threadIdx.x;
@@ -313,12 +314,12 @@ k_pow2_sum(const XYZZ<F>* __restrict__ V, int n, Fr k_mont, XYZZ<F>* __restrict_
       x = V[p];
     }
     if (!x.is_inf())
-      for (int i = 0; i < p; i++) x = dbl_cold(x);
+      for (int i = 0; i < p; i++) x = dbl(x);  // inlined: the chain of p doublings is the critical path
   }
   tmp[p] = x;
   __syncthreads();
   for (int s = 256; s > 0; s >>= 1) {
-    if (p < s) tmp[p] = add_cold(tmp[p], tmp[p + s]);
+    if (p < s && p + s < POW2_THREADS) tmp[p] = add_cold(tmp[p], tmp[p + s]);
     __syncthreads();
   }
   if (p == 0) *out = tmp[0];
@@ -371,12 +372,12 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   const int nbits = p.W * p.c;  // <= 255 + c - 1 < 512
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
   k_bucket_bits<F, BT><<<nbits, BT, 0, st>>>(buckets, p.c, p.B, segR);
-  k_pow2_sum<F, false><<<1, 512, 0, st>>>(segR, nbits, Fr::zero(), segS, out);
+  k_pow2_sum<F, false><<<1, POW2_THREADS, 0, st>>>(segR, nbits, Fr::zero(), segS, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st) {
-  k_pow2_sum<Fq, true><<<1, 512, 0, st>>>(point, 256, k_mont, reinterpret_cast<G1XYZZ*>(s.segS), out);
+  k_pow2_sum<Fq, true><<<1, POW2_THREADS, 0, st>>>(point, 256, k_mont, reinterpret_cast<G1XYZZ*>(s.segS), out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

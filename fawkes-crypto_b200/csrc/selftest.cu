@@ -43,6 +43,42 @@ __global__ void k_probe_imad(uint64_t* out, uint32_t seed, int iters) {
   if (s == 0x1234567812345678ull) out[0] = s;  // keep the loop alive
 }
 
+// carry-chained wide MACs exactly as the Montgomery rows issue them (IMAD.WIDE.U32.X)
+__global__ void k_probe_madc(uint32_t* out, uint32_t seed, int iters) {
+#if defined(__CUDA_ARCH__)
+  uint32_t X[4][9];
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 9; i++) X[c][i] = seed + c * 9 + i + threadIdx.x;
+  uint32_t a0 = seed | 1, a1 = seed * 3 + 1, a2 = seed * 5 + blockIdx.x, a3 = seed * 7 + threadIdx.x, t = seed * 11 + 5;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) ptx::mad_chain(X[c], a0, a1, a2, a3, t + c);
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 9; i++) s ^= X[c][i];
+  if (s == 0x12345678u) out[0] = s;
+#endif
+}
+
+template <int VARIANT>
+__global__ void k_probe_fr_mul_v(Fr* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fr x = Fr::one(), y = Fr::r2();
+  x.v[0] += threadIdx.x;
+  y.v[1] ^= blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+    if (VARIANT == 0) { x = mul_ptx(x, y); y = mul_ptx(y, x); }
+    else { x = mul_c(x, y); y = mul_c(y, x); }
+  }
+  if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
+#endif
+}
+
 __global__ void k_probe_fr_mul(Fr* out, int iters) {
   Fr x = Fr::one(), y = Fr::r2();
   x.v[0] += threadIdx.x;
@@ -228,6 +264,40 @@ int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) {
     if (rep > 0) best = std::max(best, rate);
   }
   *mac_per_s = best;
+  cudaFree(d);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return FB_OK;
+}
+
+// which: 0 carry-chained wide MAC rate (MAC/s), 1 mul_ptx rate, 2 mul_c rate (mul/s);
+// threads per block and blocks per SM selectable to see the occupancy dependence
+int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, double* per_s) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !per_s) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  void* d;
+  FB_CUDA(cudaMalloc(&d, 64));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = 148 * blocks_per_sm;
+  const int iters = which == 0 ? 1024 : 512;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, ctx->stream);
+    if (which == 0) k_probe_madc<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, 777u + rep, iters);
+    else if (which == 1) k_probe_fr_mul_v<0><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
+    else k_probe_fr_mul_v<1><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
+    cudaEventRecord(e1, ctx->stream);
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double work = which == 0 ? (double)iters * 4 * 4 : (double)iters * 2;
+    double rate = (double)blocks * threads * work / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  *per_s = best;
   cudaFree(d);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);

@@ -239,7 +239,7 @@ class Parameters:
 
     def __init__(self, bellman_bytes: bytes, num_gates: int, gates_blob: bytes, const_tracker=(),
                  circuit: Optional[Circuit] = None):
-        self.bellman_bytes = bellman_bytes
+        self.bellman_bytes = bellman_bytes      # bytes, or a uint8 numpy array for multi-GiB keys
         self.num_gates = num_gates
         self.gates_blob = gates_blob
         self.const_tracker = list(const_tracker)
@@ -251,7 +251,8 @@ class Parameters:
     def write(self) -> bytes:
         bv = _bitvec_to_bytes(self.const_tracker)
         return (struct.pack("<I", self.num_gates) + struct.pack("<I", len(self.gates_blob)) + self.gates_blob +
-                struct.pack("<I", len(self.const_tracker)) + struct.pack("<I", len(bv)) + bv + self.bellman_bytes)
+                struct.pack("<I", len(self.const_tracker)) + struct.pack("<I", len(bv)) + bv +
+                bytes(self.bellman_bytes))
 
     @classmethod
     def read(cls, data: bytes, disallow_points_at_infinity: bool = False, checked: bool = True) -> "Parameters":
@@ -297,8 +298,8 @@ class Parameters:
         return self._sections()["l"][1]
 
     def get_vk(self) -> VK:                    # mod.rs:142-144
-        b = self.bellman_bytes
         n_ic = self._sections()["n_ic"]
+        b = bytes(self.bellman_bytes[:580 + 64 * n_ic])
         return VK(_g1_from_be(b[0:64]), _g2_from_be(b[128:256]), _g2_from_be(b[256:384]),
                   _g2_from_be(b[448:576]), [_g1_from_be(b[580 + 64 * i:644 + 64 * i]) for i in range(n_ic)])
 
@@ -356,7 +357,9 @@ def setup(circuit: Circuit, ctx: Context, trapdoor: Optional[Sequence[int]] = No
     out, n = C.c_void_p(), C.c_size_t()
     nv.check(nv.lib.fb_setup(ctx.handle, circuit.handle, nv.ptr(tda), C.byref(out), C.byref(n)))
     try:
-        data = C.string_at(out, n.value)
+        # ctypes.string_at takes a C int length: copy by hand so keys beyond 2 GiB survive
+        data = np.empty(n.value, dtype=np.uint8)
+        C.memmove(data.ctypes.data, out, n.value)
     finally:
         nv.lib.fb_free(out)
     ng = circuit.shape()["n_gates"] if num_gates is None else num_gates

@@ -71,6 +71,7 @@ SIGNATURES = {
     "fb_test_msm": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp, C.c_int, f32p]),
     "fb_test_fixed_base": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp]),
     "fb_probe_imad": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "fb_probe_rate": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "fb_probe_fr_mul": (C.c_int, [vp, C.POINTER(C.c_double)]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

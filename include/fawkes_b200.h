@@ -167,6 +167,9 @@ int fb_test_fixed_base(fb_ctx* ctx, int group, const uint64_t* scalars, uint64_t
                        uint8_t* out_raw);
 /* IMAD-pipe roofline probe: returns 32x32->64 multiply-accumulates per second */
 int fb_probe_imad(fb_ctx* ctx, double* mac_per_s);
+/* which: 0 carry-chained wide MACs (as issued by the Montgomery rows) per second, 1 PTX Fr
+ * multiplies per second, 2 portable-C Fr multiplies per second */
+int fb_probe_rate(fb_ctx* ctx, int which, int threads, int blocks_per_sm, double* per_s);
 /* Fr multiplies per second (register resident, dependent chains across many warps) */
 int fb_probe_fr_mul(fb_ctx* ctx, double* mul_per_s);
 

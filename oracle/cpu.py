@@ -55,7 +55,8 @@ def prove(params: bytes, n_gates: int, n_in: int, n_aux: int, rowptr, col, coef,
     m = max(m, 2)
     h = np.zeros((m - 1, 4), dtype=np.uint64) if want_h else None
     st = (C.c_double * 4)()
-    rc = L.oracle_groth16_prove(C.c_char_p(params), C.c_size_t(len(params)), C.c_uint32(n_gates), C.c_uint32(n_in),
+    pbuf = np.frombuffer(params, dtype=np.uint8) if isinstance(params, (bytes, bytearray)) else np.ascontiguousarray(params, dtype=np.uint8)
+    rc = L.oracle_groth16_prove(C.c_void_p(pbuf.ctypes.data), C.c_size_t(pbuf.size), C.c_uint32(n_gates), C.c_uint32(n_in),
                                 C.c_uint32(n_aux), arr(rp), arr(cl), arr(cf), C.c_void_p(inputs.ctypes.data),
                                 C.c_void_p(aux.ctypes.data), C.c_void_p(r.ctypes.data), C.c_void_p(s.ctypes.data),
                                 C.c_int(nthreads), C.c_void_p(proof.ctypes.data),

@@ -48,7 +48,7 @@ def test_setup_matches_oracle_bytes(ctx, n_rows):
     gates, inp, aux, td, r, s, P = oracle_case(n_rows, seed)
     circ = fb.Circuit.synthetic(n_rows, seed)
     params = fb.setup(circ, ctx, trapdoor=[td.alpha, td.beta, td.gamma, td.delta, td.tau])
-    assert params.bellman_bytes == codec.bellman_params_bytes(P)
+    assert bytes(params.bellman_bytes) == codec.bellman_params_bytes(P)
 
 
 def test_prove_synthetic_2_16_scalar_identity_and_verify(ctx):
