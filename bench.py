@@ -191,7 +191,18 @@ def run_ours(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at first use: keep stdout for the JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     torch.cuda.set_device(local)
     ctx = fb.Context(local)
     circ, params, tdi, setup_s = make_case(fb, ctx, args.log_rows)
@@ -287,6 +298,10 @@ def run_ours(args):
     ok = True
     if rank == 0:
         ok = fb.verify(params.get_vk(), fb.Proof.from_raw(proof.tobytes()), wi[1:])
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     sec = t_value / args.steps
