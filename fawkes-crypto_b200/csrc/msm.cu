@@ -40,7 +40,7 @@ int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
     MsmPlan p = MsmPlan::make((uint32_t)sizes[i]);
     ent = std::max<uint64_t>(ent, sizes[i] * p.W);
     bk = std::max<uint64_t>(bk, p.nbuckets());
-    tk = std::max<uint64_t>(tk, ((sizes[i] * p.W) >> p.task_log) + p.nbuckets());
+    tk = std::max<uint64_t>(tk, ((sizes[i] * p.W) >> p.task_log) + p.nbuckets() + 2);
   }
   cap_entries = ent;
   cap_buckets = bk;
@@ -181,37 +181,39 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
 }
 
 // ------------------------------------------------------------ accumulate ---
-// Bucket runs are cut into tasks of at most T = 2^task_log entries so that a bucket holding
-// a large share of the points (top window, witnesses full of 0/1) does not serialise.
-__global__ void k_task_count(const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
-                             uint32_t* __restrict__ ntasks) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > nb) return;
-  if (b == nb) { ntasks[b] = 0; return; }
-  const uint32_t cnt = offsets[b + 1] - offsets[b];
-  ntasks[b] = (cnt + (1u << task_log) - 1) >> task_log;
-}
-
+// Equal-length tasks: thread t accumulates the sorted entries [t*T, (t+1)*T), T = 2^task_log, and
+// flushes a partial sum whenever the bucket changes.  Every thread performs exactly T mixed adds
+// (no divergence in trip count, no matter how skewed the digits are: a bucket holding a third of
+// the points is simply spread over thousands of threads).  The partial of (bucket b, thread t)
+// lives at index b + t: bucket b owns the contiguous slots b + floor(start_b / T) .. b +
+// floor((end_b - 1) / T), so no second scan is needed to find them.
 template <class F>
 __global__ void __launch_bounds__(128)
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ task_off,
-             uint32_t nb, int task_log, XYZZ<F>* __restrict__ partials) {
+             const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
+             XYZZ<F>* __restrict__ partials) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= task_off[nb]) return;
-  // bucket b with task_off[b] <= t < task_off[b+1]
-  uint32_t lo = 0, hi = nb;  // invariant: task_off[lo] <= t < task_off[hi]
+  const uint32_t total = offsets[nb];
+  const uint32_t start = t << task_log;
+  if (start >= total) return;
+  const uint32_t end = min(start + (1u << task_log), total);
+  // bucket containing entry `start`: largest b with offsets[b] <= start
+  uint32_t lo = 0, hi = nb;
   while (hi - lo > 1) {
     const uint32_t mid = (lo + hi) >> 1;
-    if (task_off[mid] <= t) lo = mid; else hi = mid;
+    if (offsets[mid] <= start) lo = mid; else hi = mid;
   }
-  const uint32_t b = lo;
-  const uint32_t start = offsets[b] + ((t - task_off[b]) << task_log);
-  const uint32_t end = min(start + (1u << task_log), offsets[b + 1]);
+  uint32_t b = lo;
+  uint32_t bend = offsets[b + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
   uint32_t e = sorted[start];
   Affine<F> nxt = bases[e & 0x7fffffffu];
   for (uint32_t p = start; p < end; p++) {
+    if (p >= bend) {  // bucket boundary: flush and move on (empty buckets are skipped)
+      partials[b + t] = acc;
+      acc = XYZZ<F>::inf();
+      do { b++; bend = offsets[b + 1]; } while (p >= bend);
+    }
     Affine<F> cur = nxt;
     const uint32_t sign = e >> 31;
     if (p + 1 < end) {
@@ -221,38 +223,40 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     if (sign) cur.y = neg(cur.y);
     acc = add_mixed(acc, cur);
   }
-  partials[t] = acc;
+  partials[b + t] = acc;
 }
 
-// bucket = sum of its task partials; buckets with more than MSM_HEAVY partials are queued
+// bucket = sum of its partials; buckets with more than MSM_HEAVY partials are queued
 template <class F>
 __global__ void __launch_bounds__(128)
-k_bucket_gather(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ task_off,
-                uint32_t nb, XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy) {
+k_bucket_gather(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ offsets,
+                uint32_t nb, int task_log, XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nb) return;
-  const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
-  if (t1 - t0 > MSM_HEAVY) {
+  const uint32_t s = offsets[b], e = offsets[b + 1];
+  if (s == e) { buckets[b] = XYZZ<F>::inf(); return; }
+  const uint32_t t0 = s >> task_log, t1 = (e - 1) >> task_log;
+  if (t1 - t0 + 1 > MSM_HEAVY) {
     heavy[1 + atomicAdd(&heavy[0], 1u)] = b;
     return;
   }
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t t = t0; t < t1; t++) acc = add_cold(acc, partials[t]);
+  XYZZ<F> acc = partials[b + t0];
+  for (uint32_t t = t0 + 1; t <= t1; t++) acc = add_cold(acc, partials[b + t]);
   buckets[b] = acc;
 }
 
 // one CTA per queued bucket: strided partial sums then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(MSM_HEAVY_THREADS)
-k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ task_off,
-               const uint32_t* __restrict__ heavy, XYZZ<F>* __restrict__ buckets) {
+k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ offsets,
+               int task_log, const uint32_t* __restrict__ heavy, XYZZ<F>* __restrict__ buckets) {
   __shared__ XYZZ<F> sh[MSM_HEAVY_THREADS];
   const uint32_t count = heavy[0];
   for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
     const uint32_t b = heavy[1 + i];
-    const uint32_t t0 = task_off[b], t1 = task_off[b + 1];
+    const uint32_t t0 = offsets[b] >> task_log, t1 = (offsets[b + 1] - 1) >> task_log;
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += MSM_HEAVY_THREADS) acc = add_cold(acc, partials[t]);
+    for (uint32_t t = t0 + threadIdx.x; t <= t1; t += MSM_HEAVY_THREADS) acc = add_cold(acc, partials[b + t]);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = MSM_HEAVY_THREADS / 2; s > 0; s >>= 1) {
@@ -351,24 +355,17 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
   XYZZ<F>* segS = reinterpret_cast<XYZZ<F>*>(s.segS);
   XYZZ<F>* partials = reinterpret_cast<XYZZ<F>*>(s.partials);
-  if (!reuse_sort) {
-    k_task_count<<<(nb + 1 + 255) / 256, 256, 0, st>>>(s.offsets, nb, p.task_log, s.ntasks);
-    const unsigned sb2 = (nb + 1 + 1023) / 1024;
-    k_scan_block<<<sb2, 1024, 0, st>>>(s.ntasks, s.task_off, s.blocksums, nb + 1);
-    k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb2);
-    k_scan_add<<<sb2, 1024, 0, st>>>(s.task_off, nullptr, s.blocksums, nb + 1);
-  }
-  const uint64_t max_tasks = (((uint64_t)p.n * p.W) >> p.task_log) + nb;
-  if (max_tasks > s.cap_tasks) return -4;
+  const uint64_t max_threads = (((uint64_t)p.n * p.W) >> p.task_log) + 1;
+  if (max_threads + nb > s.cap_tasks) return -4;
   cudaMemsetAsync(s.heavy, 0, 4, st);
   const int kind = sizeof(F) == sizeof(Fq) ? KSTAT_ACC_G1 : KSTAT_ACC_G2;
   kstat_begin(kind, st);
-  k_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, s.task_off,
-                                                                     nb, p.task_log, partials);
+  k_accumulate<F><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb,
+                                                                       p.task_log, partials);
   kstat_end(kind, st);
-  count_launch(reuse_sort ? 5 : 14);
-  k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.task_off, nb, buckets, s.heavy);
-  k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.task_off, s.heavy, buckets);
+  count_launch(reuse_sort ? 5 : 10);
+  k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.offsets, nb, p.task_log, buckets, s.heavy);
+  k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.offsets, p.task_log, s.heavy, buckets);
   const int nbits = p.W * p.c;  // <= 255 + c - 1 < 512
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
   k_bucket_bits<F, BT><<<nbits, BT, 0, st>>>(buckets, p.c, p.B, segR);

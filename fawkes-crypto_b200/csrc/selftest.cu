@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "internal.h"
+#include "ff29.cuh"
 
 namespace fb {
 
@@ -26,6 +27,38 @@ __global__ void k_field_op(int op, const Fp<C>* a, const Fp<C>* b, Fp<C>* out, u
 }
 
 // dependent-free IMAD.WIDE accumulate streams: 8 independent accumulators per thread
+// same, but every MAC reads its own multiplier register too (three distinct register operands)
+__global__ void k_probe_imad3(uint64_t* out, uint32_t seed, int iters) {
+  uint32_t a[8], b[8];
+  uint64_t acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { acc[j] = j + threadIdx.x; a[j] = seed * (2 * j + 3) + threadIdx.x; b[j] = seed * (2 * j + 5) + blockIdx.x; }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(b[(j + 3) & 7]));
+    }
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= acc[j];
+  if (s == 0x1234567812345678ull) out[0] = s;
+}
+// one accumulator, distinct operands: the dependent chain a column sum forms
+__global__ void k_probe_imad_chain(uint64_t* out, uint32_t seed, int iters) {
+  uint32_t a[8], b[8];
+  uint64_t acc = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { a[j] = seed * (2 * j + 3) + threadIdx.x; b[j] = seed * (2 * j + 5) + blockIdx.x; }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a[j]), "r"(b[(j + 3) & 7]));
+    }
+  }
+  if (acc == 0x1234567812345678ull) out[0] = acc;
+}
+
 __global__ void k_probe_imad(uint64_t* out, uint32_t seed, int iters) {
   uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
   uint64_t acc[8];
@@ -65,6 +98,35 @@ __global__ void k_probe_madc(uint32_t* out, uint32_t seed, int iters) {
 #endif
 }
 
+// MAC stream shapes: 0 = 8 accumulators, distinct a and b per MAC; 1 = one accumulator (dependent
+// chain), distinct operands; 2 = 8 accumulators, a distinct, b shared (operand reuse)
+template <int SHAPE>
+__global__ void k_probe_mac_shape(uint64_t* out, uint32_t seed, int iters) {
+  uint32_t a0 = seed * 3 + threadIdx.x, a1 = seed * 5 + 1, a2 = seed * 7 + 2, a3 = seed * 11 + 3, a4 = seed * 13 + 4,
+           a5 = seed * 17 + 5, a6 = seed * 19 + 6, a7 = seed * 23 + 7;
+  uint32_t b0 = seed * 29 + blockIdx.x, b1 = seed * 31 + 1, b2 = seed * 37 + 2, b3 = seed * 41 + 3, b4 = seed * 43 + 4,
+           b5 = seed * 47 + 5, b6 = seed * 53 + 6, b7 = seed * 59 + 7;
+  uint64_t c0 = 0, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+  for (int i = 0; i < iters; i++) {
+    if (SHAPE == 0) {  // 8 accumulators, all operands distinct
+      c0 += (uint64_t)a0 * b3; c1 += (uint64_t)a1 * b4; c2 += (uint64_t)a2 * b5; c3 += (uint64_t)a3 * b6;
+      c4 += (uint64_t)a4 * b7; c5 += (uint64_t)a5 * b0; c6 += (uint64_t)a6 * b1; c7 += (uint64_t)a7 * b2;
+    } else if (SHAPE == 1) {  // one accumulator: a dependent chain
+      c0 += (uint64_t)a0 * b3; c0 += (uint64_t)a1 * b4; c0 += (uint64_t)a2 * b5; c0 += (uint64_t)a3 * b6;
+      c0 += (uint64_t)a4 * b7; c0 += (uint64_t)a5 * b0; c0 += (uint64_t)a6 * b1; c0 += (uint64_t)a7 * b2;
+    } else if (SHAPE == 2) {  // 8 accumulators, shared multiplier (operand reuse)
+      c0 += (uint64_t)a0 * b0; c1 += (uint64_t)a1 * b0; c2 += (uint64_t)a2 * b0; c3 += (uint64_t)a3 * b0;
+      c4 += (uint64_t)a4 * b0; c5 += (uint64_t)a5 * b0; c6 += (uint64_t)a6 * b0; c7 += (uint64_t)a7 * b0;
+    } else {  // two accumulators, distinct operands
+      c0 += (uint64_t)a0 * b3; c1 += (uint64_t)a1 * b4; c0 += (uint64_t)a2 * b5; c1 += (uint64_t)a3 * b6;
+      c0 += (uint64_t)a4 * b7; c1 += (uint64_t)a5 * b0; c0 += (uint64_t)a6 * b1; c1 += (uint64_t)a7 * b2;
+    }
+    a0 += 3; b0 ^= a0;  // two ALU ops per 8 MACs keep the loop body live
+  }
+  uint64_t s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  if (s == 0x1234567812345678ull) out[0] = s;
+}
+
 template <int VARIANT>
 __global__ void k_probe_fr_mul_v(Fr* out, int iters) {
 #if defined(__CUDA_ARCH__)
@@ -77,6 +139,18 @@ __global__ void k_probe_fr_mul_v(Fr* out, int iters) {
   }
   if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
 #endif
+}
+// lazy 29-bit multiplier: VARIANT 0 mul/mul, 1 sqr + add + sub (the non-multiply mix of a point add)
+template <int VARIANT>
+__global__ void k_probe_fr29(Fr* out, int iters) {
+  Fr29 x = Fr29::one(), y = Fr29::one();
+  x.l[0] += threadIdx.x;
+  y.l[1] ^= blockIdx.x & 0xff;
+  for (int i = 0; i < iters; i++) {
+    if (VARIANT == 0) { x = mul(x, y); y = mul(y, x); }
+    else { x = sqr(x); y = add(y, x); x = sub(x, y); }
+  }
+  if (x.l[0] == 0x12345678u && y.l[3] == 0x9abcdefu) out[0].v[0] = x.l[2];
 }
 
 __global__ void k_probe_fr_mul(Fr* out, int iters) {
@@ -288,12 +362,20 @@ int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, doubl
     cudaEventRecord(e0, ctx->stream);
     if (which == 0) k_probe_madc<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, 777u + rep, iters);
     else if (which == 1) k_probe_fr_mul_v<0><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
+    else if (which == 9) k_probe_imad3<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 10) k_probe_imad_chain<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 5) k_probe_mac_shape<0><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 6) k_probe_mac_shape<1><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 7) k_probe_mac_shape<2><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 8) k_probe_mac_shape<3><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
+    else if (which == 3) k_probe_fr29<0><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
+    else if (which == 4) k_probe_fr29<1><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
     else k_probe_fr_mul_v<1><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
     cudaEventRecord(e1, ctx->stream);
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    double work = which == 0 ? (double)iters * 4 * 4 : (double)iters * 2;
+    double work = which == 0 ? (double)iters * 4 * 4 : (which >= 5 ? (double)iters * 8 : (double)iters * 2);
     double rate = (double)blocks * threads * work / (ms * 1e-3);
     if (rep > 0) best = std::max(best, rate);
   }
