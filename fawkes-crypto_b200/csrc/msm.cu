@@ -12,9 +12,10 @@ MsmPlan MsmPlan::make(uint32_t n) {
   p.n = n;
   int lg = 0;
   while ((2u << lg) <= n && lg < 31) lg++;
-  int c = lg - 6;
+  // window: accumulation costs n*W mixed adds, reduction ~2.6 * W * 2^(c-1) full adds
+  int c = lg - 4;
   if (c < 4) c = 4;
-  if (c > 16) c = 16;
+  if (c > 20) c = 20;
   if (const char* e = getenv("FB_MSM_C")) {
     int v = atoi(e);
     if (v >= 2 && v <= 24) c = v;
@@ -22,7 +23,7 @@ MsmPlan MsmPlan::make(uint32_t n) {
   p.c = c;
   p.W = (255 + c - 1) / c;
   p.B = 1u << (c - 1);
-  p.seg_log = c - 1 < 5 ? c - 1 : 5;
+  p.seg_log = c - 1 < 5 ? c - 1 : 5;   // K = 32 buckets per reduce segment (>= 2: c >= 4)
   // task size: enough tasks to fill the chip, at most 256 adds per thread
   uint64_t want = ((uint64_t)n * p.W) >> 18;
   int tl = 4;
@@ -51,9 +52,9 @@ int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
   if (cudaMalloc(&blocksums, ((bk + 1023) / 1024 + 1) * 4) != cudaSuccess) return -1;
   if (cudaMalloc(&sorted, std::max<uint64_t>(ent, 1) * 4) != cudaSuccess) return -1;
   if (cudaMalloc(&buckets, bk * psz) != cudaSuccess) return -1;
-  if (cudaMalloc(&segR, 512 * psz) != cudaSuccess) return -1;  // U[p], p < W*c
-  if (cudaMalloc(&segS, 512 * psz) != cudaSuccess) return -1;  // tree scratch of k_pow2_sum
-  if (cudaMalloc(&winsum, 256 * psz) != cudaSuccess) return -1;
+  if (cudaMalloc(&segR, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment weighted sums (K >= 2)
+  if (cudaMalloc(&segS, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment plain sums
+  if (cudaMalloc(&winsum, 1024 * psz) != cudaSuccess) return -1;        // V[p] then the tree scratch of k_pow2_sum
   // task decomposition of the bucket runs (load balancing under skewed digits)
   cap_tasks = tk + 1;
   if (cudaMalloc(&ntasks, (bk + 1) * 4) != cudaSuccess) return -1;
@@ -269,40 +270,63 @@ k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict_
 }
 
 // ---------------------------------------------------------------- reduce ---
-// sum_w 2^(c w) sum_j (j+1) B[w][j]  is evaluated bit-wise: with p = c w + k,
-//   U[p] = sum of the buckets of window w whose value (j+1) has bit k set      (plain sums)
-//   result = sum_p 2^p U[p]
-// k_bucket_bits: one CTA per p, strided partial sums + shared-memory tree (no serial running sum).
-// k_pow2_sum:    thread p doubles its term p times, then a tree over the W*c terms; the depth is
-//                the unavoidable ~255 doublings, everything else is parallel.
+// sum_w 2^(c w) sum_j (j+1) B[w][j]  in three parallel steps (no long serial running sum):
+//  1. k_bucket_segments: segments of K = 2^seg_log buckets, one thread each, short running sums:
+//        R_s = sum_t (t+1) B[sK+t],  S_s = sum_t B[sK+t]      so that  sum_j (j+1) B_j = sum_s R_s + K sum_s s S_s
+//  2. k_segment_bits: sum_s s S_s is evaluated bit-wise, V[c w + seg_log + k] = sum of S_s with bit k of
+//     s set (one CTA per (w, k), tree), and V[c w] = sum_s R_s
+//  3. k_pow2_sum: result = sum_p 2^p V[p]: thread p doubles p times, then a tree.  The only serial
+//     chain left is the unavoidable ~255 doublings.
+// Cost ~2 adds per bucket, so large windows (few digits per scalar) stay cheap to reduce.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_segments(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, int seg_log,
+                  XYZZ<F>* __restrict__ segR, XYZZ<F>* __restrict__ segS) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsegs) return;
+  const XYZZ<F>* bk = buckets + ((uint64_t)s << seg_log);
+  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
+  for (int t = (1 << seg_log) - 1; t >= 0; t--) {
+    run = add(run, bk[t]);   // inlined: 2K dependent adds are this kernel's critical path
+    tot = add_cold(tot, run);
+  }
+  segR[s] = tot;
+  segS[s] = run;
+}
+
+// grid = W * (1 + sbits) CTAs, sbits = bits of the segment index.  CTA (w, 0): V[c w] = sum_s R_s;
+// CTA (w, 1 + k): V[c w + seg_log + k] = sum of S_s over segments whose index has bit k set.
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k_bucket_bits(const XYZZ<F>* __restrict__ buckets, int c, uint32_t B, XYZZ<F>* __restrict__ U) {
+k_segment_bits(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ segS, int c, int seg_log,
+               int sbits, XYZZ<F>* __restrict__ V) {
   __shared__ XYZZ<F> sh[THREADS];
-  const int p = blockIdx.x, w = p / c, k = p % c;
-  const XYZZ<F>* bk = buckets + (uint64_t)w * B;
+  const int per_w = 1 + sbits;
+  const int w = blockIdx.x / per_w, which = blockIdx.x % per_w;
+  const uint32_t segs = 1u << sbits;
   XYZZ<F> acc = XYZZ<F>::inf();
-  // values v = j+1 in [1, B] with bit k set: enumerate t in [0, B/2] -> v
-  if (k == c - 1) {
-    if (threadIdx.x == 0) acc = bk[B - 1];  // only v = B = 2^(c-1) has bit c-1
+  if (which == 0) {
+    const XYZZ<F>* R = segR + (uint64_t)w * segs;
+    for (uint32_t s = threadIdx.x; s < segs; s += THREADS) acc = add_cold(acc, R[s]);
   } else {
+    const int k = which - 1;
+    const XYZZ<F>* S = segS + (uint64_t)w * segs;
     const uint32_t low_mask = (1u << k) - 1;
-    for (uint32_t t = threadIdx.x; t < (B >> 1); t += THREADS) {
-      // insert a 1 at bit position k of t
-      const uint32_t v = ((t & ~low_mask) << 1) | (1u << k) | (t & low_mask);
-      if (v <= B) acc = add_cold(acc, bk[v - 1]);
+    for (uint32_t t = threadIdx.x; t < (segs >> 1); t += THREADS) {
+      const uint32_t sidx = ((t & ~low_mask) << 1) | (1u << k) | (t & low_mask);  // insert a 1 at bit k
+      acc = add_cold(acc, S[sidx]);
     }
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
-  for (int s = THREADS / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + s]);
+  for (int st = THREADS / 2; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + st]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) U[p] = sh[0];
+  if (threadIdx.x == 0) V[c * w + (which == 0 ? 0 : seg_log + which - 1)] = sh[0];
 }
 
-constexpr int POW2_THREADS = 288;  // >= W*c for every plan (255 + c - 1 <= 278)
+constexpr int POW2_THREADS = 288;  // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
 // out = sum_{p < n} 2^p V[p]  (n <= POW2_THREADS).  SCALAR: V[p] = bit p of k ? *one : infinity.
 template <class F, bool SCALAR>
 __global__ void __launch_bounds__(POW2_THREADS)
@@ -363,18 +387,25 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   k_accumulate<F><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb,
                                                                        p.task_log, partials);
   kstat_end(kind, st);
-  count_launch(reuse_sort ? 5 : 10);
+  count_launch(reuse_sort ? 6 : 11);
   k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.offsets, nb, p.task_log, buckets, s.heavy);
   k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.offsets, p.task_log, s.heavy, buckets);
-  const int nbits = p.W * p.c;  // <= 255 + c - 1 < 512
+  const int nbits = p.W * p.c;  // <= 255 + c - 1 <= POW2_THREADS
+  const int sbits = p.c - 1 - p.seg_log;  // bits of the segment index within a window
+  const uint32_t nsegs = nb >> p.seg_log;
+  XYZZ<F>* V = reinterpret_cast<XYZZ<F>*>(s.winsum);
+  XYZZ<F>* tree = V + POW2_THREADS;
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
-  k_bucket_bits<F, BT><<<nbits, BT, 0, st>>>(buckets, p.c, p.B, segR);
-  k_pow2_sum<F, false><<<1, POW2_THREADS, 0, st>>>(segR, nbits, Fr::zero(), segS, out);
+  cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * POW2_THREADS, st);
+  k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
+  k_segment_bits<F, BT><<<p.W * (1 + sbits), BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, V);
+  k_pow2_sum<F, false><<<1, POW2_THREADS, 0, st>>>(V, nbits, Fr::zero(), tree, out);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st) {
-  k_pow2_sum<Fq, true><<<1, POW2_THREADS, 0, st>>>(point, 256, k_mont, reinterpret_cast<G1XYZZ*>(s.segS), out);
+  k_pow2_sum<Fq, true><<<1, POW2_THREADS, 0, st>>>(point, 256, k_mont,
+                                                   reinterpret_cast<G1XYZZ*>(s.winsum) + POW2_THREADS, out);
   count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -16,8 +16,9 @@
 //                      per-bucket task counts maps task -> bucket); one thread per task,
 //                      XYZZ mixed adds, next base prefetched while the current add runs;
 //                      k_bucket_gather / k_bucket_heavy fold task partials into buckets
-//   5. k_bucket_bits   U[p] = sum of the buckets whose value has bit (p mod c) set, window p / c
-//   6. k_pow2_sum      sum_p 2^p U[p]: thread p doubles p times, then a tree
+//   5. k_bucket_segments / k_segment_bits   per-segment short running sums, then the segment
+//                      sums combined bit-wise into V[p] (weight 2^p)
+//   6. k_pow2_sum      sum_p 2^p V[p]: thread p doubles p times, then a tree
 // Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
 #pragma once
 #include <cuda_runtime.h>
@@ -51,9 +52,9 @@ struct MsmScratch {
   uint32_t* blocksums = nullptr;
   uint32_t* sorted = nullptr;   // [n * W]
   void* buckets = nullptr;      // [nbuckets] XYZZ (sized for G2)
-  void* segR = nullptr;         // [512] XYZZ: per-bit sums U[p]
-  void* segS = nullptr;         // [512] XYZZ: tree scratch
-  void* winsum = nullptr;       // [W] XYZZ
+  void* segR = nullptr;         // [nsegs] XYZZ: per-segment weighted sums
+  void* segS = nullptr;         // [nsegs] XYZZ: per-segment plain sums
+  void* winsum = nullptr;       // [1024] XYZZ: V[p] (first 288) and the doubling-tree scratch
   uint32_t* ntasks = nullptr;   // [nbuckets + 1]
   uint32_t* task_off = nullptr; // [nbuckets + 1]
   void* partials = nullptr;     // [cap_tasks] XYZZ
