@@ -66,6 +66,7 @@ static void pk_release(ProvingKey* pk) {
   for (auto& x : pk->msm) x.release();
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
+  for (auto& e : pk->msm_done) if (e) cudaEventDestroy(e);
   delete pk;
 }
 
@@ -205,8 +206,9 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     pk_release(pk);
     return FB_ERR_CUDA;
   }
-  PK_CUDA(cudaMalloc(&pk->results, 7 * sizeof(G2XYZZ)));
-  PK_CUDA(cudaMallocHost(&pk->results_host, 7 * sizeof(G2XYZZ)));
+  PK_CUDA(cudaMalloc(&pk->results, 5 * MSM_VBITS * sizeof(G2XYZZ)));
+  for (auto& e : pk->msm_done) PK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  PK_CUDA(cudaMallocHost(&pk->results_host, 5 * MSM_VBITS * sizeof(G2XYZZ)));
   PK_CUDA(cudaStreamSynchronize(st));
   *out = pk;
   return FB_OK;
@@ -228,10 +230,17 @@ struct VkPoints {
   G1Affine alpha_g1, beta_g1, delta_g1;
   G2Affine beta_g2, delta_g2;
 };
+typedef XYZZ<HFq> H1;   // host G1 accumulator (64-bit limbs)
+typedef XYZZ<HFq2> H2;
+static H1 h1_from(const G1Affine& p) { return p.is_inf() ? H1::inf() : H1{HFq::from(p.x), HFq::from(p.y), HFq::one(), HFq::one()}; }
+static H2 h2_from(const G2Affine& p) { return p.is_inf() ? H2::inf() : H2{HFq2::from(p.x), HFq2::from(p.y), HFq2::one(), HFq2::one()}; }
+static G1Affine h1_affine(const H1& p) { Affine<HFq> a = to_affine(p); return {a.x.to(), a.y.to()}; }
+static G2Affine h2_affine(const H2& p) { Affine<HFq2> a = to_affine(p); return {a.x.to(), a.y.to()}; }
+
 struct FixedTerms {  // the parts of A, B, C that depend on r, s and the key only
-  G1XYZZ a;   // alpha + r*delta
-  G2XYZZ b;   // beta2 + s*delta2
-  G1XYZZ c;   // rs*delta + s*alpha + r*beta1
+  H1 a;   // alpha + r*delta
+  H2 b;   // beta2 + s*delta2
+  H1 c;   // rs*delta + s*alpha + r*beta1
   uint32_t rc[8], sc[8];
 };
 static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s[4], FixedTerms& f) {
@@ -247,55 +256,52 @@ static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s
   memcpy(sm.v, s, 32);
   Fr rs = from_mont(mul(rm, sm));
   memcpy(rsc, rs.v, 32);
-  G1XYZZ d1 = G1XYZZ::from_affine(pk->delta_g1), al = G1XYZZ::from_affine(pk->alpha_g1),
-         be1 = G1XYZZ::from_affine(pk->beta_g1);
-  G2XYZZ d2 = G2XYZZ::from_affine(pk->delta_g2);
-  f.a = add_mixed_cold(scalar_mul(d1, f.rc), pk->alpha_g1);
-  f.b = add_mixed_cold(scalar_mul(d2, f.sc), pk->beta_g2);
+  H1 d1 = h1_from(pk->delta_g1), al = h1_from(pk->alpha_g1), be1 = h1_from(pk->beta_g1);
+  H2 d2 = h2_from(pk->delta_g2);
+  f.a = add(scalar_mul(d1, f.rc), al);
+  f.b = add(scalar_mul(d2, f.sc), h2_from(pk->beta_g2));
   f.c = scalar_mul(d1, rsc);
-  f.c = add_cold(f.c, scalar_mul(al, f.sc));
-  f.c = add_cold(f.c, scalar_mul(be1, f.rc));
+  f.c = add(f.c, scalar_mul(al, f.sc));
+  f.c = add(f.c, scalar_mul(be1, f.rc));
   return FB_OK;
 }
-// sA = s*sum_a and rB1 = r*sum_b1 come from the device when available (null -> host)
-static void finish_proof(const FixedTerms& f, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
-                         const G1XYZZ& B1, const G2XYZZ& B2, const G1XYZZ* sA, const G1XYZZ* rB1,
-                         uint8_t proof_raw[256]) {
-  G1XYZZ g_a = add_cold(f.a, A);
-  G2XYZZ g_b = add_cold(f.b, B2);
-  G1XYZZ g_c = add_cold(f.c, sA ? *sA : scalar_mul(A, f.sc));
-  g_c = add_cold(g_c, rB1 ? *rB1 : scalar_mul(B1, f.rc));
-  g_c = add_cold(g_c, H);
-  g_c = add_cold(g_c, L);
-  G1Affine pa = to_affine(g_a), pc = to_affine(g_c);
-  G2Affine pb = to_affine(g_b);
+static void finish_proof(const FixedTerms& f, const H1& H, const H1& L, const H1& A, const H1& B1,
+                         const H2& B2, uint8_t proof_raw[256]) {
+  H1 g_a = add(f.a, A);
+  H2 g_b = add(f.b, B2);
+  H1 g_c = add(f.c, scalar_mul(A, f.sc));
+  g_c = add(g_c, scalar_mul(B1, f.rc));
+  g_c = add(g_c, H);
+  g_c = add(g_c, L);
+  G1Affine pa = h1_affine(g_a), pc = h1_affine(g_c);
+  G2Affine pb = h2_affine(g_b);
   memcpy(proof_raw, &pa, 64);
   memcpy(proof_raw + 64, &pb, 128);
   memcpy(proof_raw + 192, &pc, 64);
 }
-static int assemble(const VkPoints* pk, const G1XYZZ& H, const G1XYZZ& L, const G1XYZZ& A,
-                    const G1XYZZ& B1, const G2XYZZ& B2, const uint64_t r[4], const uint64_t s[4],
-                    uint8_t proof_raw[256]) {
+static int assemble(const VkPoints* pk, const H1& H, const H1& L, const H1& A, const H1& B1, const H2& B2,
+                    const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]) {
   FixedTerms f;
   int rc = fixed_terms(pk, r, s, f);
   if (rc) return rc;
-  finish_proof(f, H, L, A, B1, B2, nullptr, nullptr, proof_raw);
+  finish_proof(f, H, L, A, B1, B2, proof_raw);
   return FB_OK;
 }
 
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
 
-// device part: w already in pk->w (on the main stream).  Leaves the five XYZZ sums (+ s*A, r*B1
-// when r, s are given) in pk->results_host.  NOT synchronised on return.
-static int prove_launch(ProvingKey* pk, uint64_t* h_out, const uint64_t* r, const uint64_t* s) {
+// Result slots: five arrays of MSM_VBITS bit sums (G2-sized slots), order H L A B1 B2.
+static inline G2XYZZ* vslot(void* base, int i) { return reinterpret_cast<G2XYZZ*>(base) + (size_t)i * MSM_VBITS; }
+
+// device part: w already in pk->w (on the main stream).  Every MSM leaves its bit sums in
+// pk->results_host and records an event on its stream.  NOT synchronised on return.
+static int prove_launch(ProvingKey* pk, uint64_t* h_out) {
   Ctx* ctx = pk->ctx;
   cudaStream_t st = ctx->stream;
   cudaStream_t sL = g_serial ? st : ctx->aux[0], sA = g_serial ? st : ctx->aux[1],
                sB = g_serial ? st : ctx->aux[2];
   Timing& T = g_timing;
   const uint64_t m = pk->m;
-  G2XYZZ* res = reinterpret_cast<G2XYZZ*>(pk->results);
-  FB_CUDA(cudaMemsetAsync(res, 0, 7 * sizeof(G2XYZZ), st));
   cudaEventRecord(T.ev[1], st);  // witness resident
   if (!g_serial) {
     for (int i = 0; i < 3; i++) FB_CUDA(cudaStreamWaitEvent(ctx->aux[i], T.ev[1], 0));
@@ -303,21 +309,24 @@ static int prove_launch(ProvingKey* pk, uint64_t* h_out, const uint64_t* r, cons
   const uint64_t nh = m - 1;
   const uint64_t h_lo = nh * pk->shard / pk->nshards;
   const uint64_t l_lo = (uint64_t)pk->n_aux * pk->shard / pk->nshards;
-  // witness-only MSMs start at once on their own streams; the G2 one first (longest tail)
-  int rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm[3], res + 4, false, sB);
-  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm[3], (G1XYZZ*)(res + 3), true, sB);
-  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm[2], (G1XYZZ*)(res + 2), false, sA);
-  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)(res + 1), false, sL);
-  if (r && s) {
-    Fr rm, sm;
-    memcpy(rm.v, r, 32);
-    memcpy(sm.v, s, 32);
-    scalar_mul_g1((const G1XYZZ*)(res + 2), sm, pk->msm[2], (G1XYZZ*)(res + 5), sA);
-    scalar_mul_g1((const G1XYZZ*)(res + 3), rm, pk->msm[3], (G1XYZZ*)(res + 6), sB);
-  }
+  auto fetch = [&](int slot, size_t bytes, cudaStream_t s, int ev) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(vslot(pk->results_host, slot), vslot(pk->results, slot), bytes,
+                                    cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaEventRecord(pk->msm_done[ev], s);
+    return e;
+  };
+  // witness-only MSMs start at once on their own streams; the G2 one first (longest)
+  int rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm[3], vslot(pk->results, 4), false, sB);
+  if (!rc) FB_CUDA(fetch(4, sizeof(G2XYZZ) * MSM_VBITS, sB, 4));
+  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm[3], (G1XYZZ*)vslot(pk->results, 3), true, sB);
+  if (!rc) FB_CUDA(fetch(3, sizeof(G1XYZZ) * MSM_VBITS, sB, 3));
+  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm[2], (G1XYZZ*)vslot(pk->results, 2), false, sA);
+  if (!rc) FB_CUDA(fetch(2, sizeof(G1XYZZ) * MSM_VBITS, sA, 2));
+  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)vslot(pk->results, 1), false, sL);
+  if (!rc) FB_CUDA(fetch(1, sizeof(G1XYZZ) * MSM_VBITS, sL, 1));
   // R1CS evaluation and the H pipeline on the main stream
   if (!rc) rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
-  if (rc > 0 || rc < 0) {
+  if (rc) {
     if (rc != FB_ERR_CUDA) set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
     return FB_ERR_CUDA;
   }
@@ -329,16 +338,10 @@ static int prove_launch(ProvingKey* pk, uint64_t* h_out, const uint64_t* r, cons
     pk->dom.bitrev(pk->scratch, pk->ev[0], st);
     FB_CUDA(cudaMemcpyAsync(h_out, pk->scratch, (m - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
   }
-  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm[0], (G1XYZZ*)(res + 0), false, st);
+  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm[0], (G1XYZZ*)vslot(pk->results, 0), false, st);
   if (rc) { set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
-  if (!g_serial) {
-    for (int i = 0; i < 3; i++) {
-      FB_CUDA(cudaEventRecord(ctx->aux_done[i], ctx->aux[i]));
-      FB_CUDA(cudaStreamWaitEvent(st, ctx->aux_done[i], 0));
-    }
-  }
+  FB_CUDA(fetch(0, sizeof(G1XYZZ) * MSM_VBITS, st, 0));
   cudaEventRecord(T.ev[4], st);
-  FB_CUDA(cudaMemcpyAsync(pk->results_host, res, 7 * sizeof(G2XYZZ), cudaMemcpyDeviceToHost, st));
   return FB_OK;
 }
 
@@ -375,32 +378,40 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));
   }
-  int rc = prove_launch(pk, h_out, partial ? nullptr : r, partial ? nullptr : s);
-  if (rc) { cudaStreamSynchronize(st); return rc; }
+  int rc = prove_launch(pk, h_out);
+  if (rc) { cudaDeviceSynchronize(); return rc; }
   // host work that needs only r, s and the key overlaps the device
   FixedTerms ft;
   VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
   int rc_fixed = partial ? FB_OK : fixed_terms(&vk, r, s, ft);
+  // finish each MSM on the host as soon as its bit sums arrive (B2, B1, A, L finish while the
+  // device still runs the H pipeline and the H MSM)
+  FB_CUDA(cudaEventSynchronize(pk->msm_done[4]));
+  H2 B2 = msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.W * pk->plan_b.c);
+  FB_CUDA(cudaEventSynchronize(pk->msm_done[3]));
+  H1 B1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.W * pk->plan_b.c);
+  FB_CUDA(cudaEventSynchronize(pk->msm_done[2]));
+  H1 A = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.W * pk->plan_a.c);
+  FB_CUDA(cudaEventSynchronize(pk->msm_done[1]));
+  H1 L = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 1), pk->plan_l.W * pk->plan_l.c);
+  FB_CUDA(cudaEventSynchronize(pk->msm_done[0]));
+  auto t1 = std::chrono::steady_clock::now();
+  H1 H = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 0), pk->plan_h.W * pk->plan_h.c);
   FB_CUDA(cudaStreamSynchronize(st));
   FB_CUDA(cudaGetLastError());
   if (rc_fixed) return rc_fixed;
-  auto t1 = std::chrono::steady_clock::now();
-  const G2XYZZ* res = reinterpret_cast<const G2XYZZ*>(pk->results_host);
-  G1XYZZ H = *(const G1XYZZ*)(res + 0), L = *(const G1XYZZ*)(res + 1), A = *(const G1XYZZ*)(res + 2),
-         B1 = *(const G1XYZZ*)(res + 3), sA = *(const G1XYZZ*)(res + 5), rB1 = *(const G1XYZZ*)(res + 6);
-  G2XYZZ B2 = res[4];
   if (partial) {
     memset(partial, 0, 640);
     G1Affine p;
-    p = to_affine(H); memcpy(partial + 0, &p, 64);
-    p = to_affine(L); memcpy(partial + 128, &p, 64);
-    p = to_affine(A); memcpy(partial + 256, &p, 64);
-    p = to_affine(B1); memcpy(partial + 384, &p, 64);
-    G2Affine q = to_affine(B2);
+    p = h1_affine(H); memcpy(partial + 0, &p, 64);
+    p = h1_affine(L); memcpy(partial + 128, &p, 64);
+    p = h1_affine(A); memcpy(partial + 256, &p, 64);
+    p = h1_affine(B1); memcpy(partial + 384, &p, 64);
+    G2Affine q = h2_affine(B2);
     memcpy(partial + 512, &q, 128);
     rc = FB_OK;
   } else {
-    finish_proof(ft, H, L, A, B1, B2, &sA, &rB1, proof_raw);
+    finish_proof(ft, H, L, A, B1, B2, proof_raw);
     rc = FB_OK;
   }
   auto t2 = std::chrono::steady_clock::now();
@@ -592,18 +603,18 @@ int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* pa
     set_error("invalid verifying-key point");
     return FB_ERR_FORMAT;
   }
-  G1XYZZ sum[4] = {G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf(), G1XYZZ::inf()};
-  G2XYZZ sum2 = G2XYZZ::inf();
+  H1 sum[4] = {H1::inf(), H1::inf(), H1::inf(), H1::inf()};
+  H2 sum2 = H2::inf();
   for (int i = 0; i < nparts; i++) {
     const uint8_t* p = partials + (size_t)i * 640;
     for (int j = 0; j < 4; j++) {
       G1Affine a;
       memcpy(&a, p + 128 * j, 64);
-      sum[j] = add_mixed_cold(sum[j], a);
+      sum[j] = add(sum[j], h1_from(a));
     }
     G2Affine q;
     memcpy(&q, p + 512, 128);
-    sum2 = add_mixed_cold(sum2, q);
+    sum2 = add(sum2, h2_from(q));
   }
   return assemble(&vk, sum[0], sum[1], sum[2], sum[3], sum2, r, s, proof_raw);
 }

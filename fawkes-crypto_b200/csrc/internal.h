@@ -10,6 +10,7 @@
 
 #include "../../include/fawkes_b200.h"
 #include "ec.cuh"
+#include "host_fq.h"
 #include "msm.cuh"
 #include "ntt.cuh"
 
@@ -82,7 +83,8 @@ struct ProvingKey {
   Fr* scratch = nullptr;   // m (h_out permutation)
   MsmScratch msm[4];       // H, L, A, B (B_g1 and B_g2 share one sort)
   MsmPlan plan_h, plan_l, plan_a, plan_b;
-  void* results = nullptr;       // 7 x G2XYZZ slots on device: H L A B1 B2 s*A r*B1
+  void* results = nullptr;       // 5 x MSM_VBITS G2XYZZ-sized slots on device: bit sums of H L A B1 B2
+  cudaEvent_t msm_done[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   void* results_host = nullptr;  // pinned
   // base-index shard handled by this key (multi-GPU): fractions [shard, shard+1)/nshards
   int shard = 0, nshards = 1;

@@ -23,7 +23,7 @@ MsmPlan MsmPlan::make(uint32_t n) {
   p.c = c;
   p.W = (255 + c - 1) / c;
   p.B = 1u << (c - 1);
-  p.seg_log = c - 1 < 5 ? c - 1 : 5;   // K = 32 buckets per reduce segment (>= 2: c >= 4)
+  p.seg_log = 3;   // K = 8 buckets per reduce segment: 16 dependent adds deep (c >= 4)
   // task size: enough tasks to fill the chip, at most 256 adds per thread
   uint64_t want = ((uint64_t)n * p.W) >> 18;
   int tl = 4;
@@ -54,7 +54,7 @@ int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
   if (cudaMalloc(&buckets, bk * psz) != cudaSuccess) return -1;
   if (cudaMalloc(&segR, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment weighted sums (K >= 2)
   if (cudaMalloc(&segS, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment plain sums
-  if (cudaMalloc(&winsum, 1024 * psz) != cudaSuccess) return -1;        // V[p] then the tree scratch of k_pow2_sum
+  winsum = nullptr;
   // task decomposition of the bucket runs (load balancing under skewed digits)
   cap_tasks = tk + 1;
   if (cudaMalloc(&ntasks, (bk + 1) * 4) != cudaSuccess) return -1;
@@ -275,8 +275,9 @@ k_bucket_heavy(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict_
 //        R_s = sum_t (t+1) B[sK+t],  S_s = sum_t B[sK+t]      so that  sum_j (j+1) B_j = sum_s R_s + K sum_s s S_s
 //  2. k_segment_bits: sum_s s S_s is evaluated bit-wise, V[c w + seg_log + k] = sum of S_s with bit k of
 //     s set (one CTA per (w, k), tree), and V[c w] = sum_s R_s
-//  3. k_pow2_sum: result = sum_p 2^p V[p]: thread p doubles p times, then a tree.  The only serial
-//     chain left is the unavoidable ~255 doublings.
+//  3. the caller copies V (<= MSM_VBITS points) to the host and evaluates sum_p 2^p V[p] by Horner
+//     there (msm_horner_host): the ~255 dependent doublings cost 0.2 ms on a CPU core against
+//     1.3 ms (G1) / 4 ms (G2) for one GPU thread, and they overlap the remaining device work.
 // Cost ~2 adds per bucket, so large windows (few digits per scalar) stay cheap to reduce.
 template <class F>
 __global__ void __launch_bounds__(128)
@@ -326,33 +327,6 @@ k_segment_bits(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ seg
   if (threadIdx.x == 0) V[c * w + (which == 0 ? 0 : seg_log + which - 1)] = sh[0];
 }
 
-constexpr int POW2_THREADS = 288;  // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
-// out = sum_{p < n} 2^p V[p]  (n <= POW2_THREADS).  SCALAR: V[p] = bit p of k ? *one : infinity.
-template <class F, bool SCALAR>
-__global__ void __launch_bounds__(POW2_THREADS)
-k_pow2_sum(const XYZZ<F>* __restrict__ V, int n, Fr k_mont, XYZZ<F>* __restrict__ tmp,
-           XYZZ<F>* __restrict__ out) {
-  const int p = threadIdx.x;
-  XYZZ<F> x = XYZZ<F>::inf();
-  if (p < n) {
-    if (SCALAR) {
-      Fr k = from_mont(k_mont);
-      if (p < 256 && ((k.v[p >> 5] >> (p & 31)) & 1)) x = V[0];
-    } else {
-      x = V[p];
-    }
-    if (!x.is_inf())
-      for (int i = 0; i < p; i++) x = dbl(x);  // inlined: the chain of p doublings is the critical path
-  }
-  tmp[p] = x;
-  __syncthreads();
-  for (int s = 256; s > 0; s >>= 1) {
-    if (p < s && p + s < POW2_THREADS) tmp[p] = add_cold(tmp[p], tmp[p + s]);
-    __syncthreads();
-  }
-  if (p == 0) *out = tmp[0];
-}
-
 // ----------------------------------------------------------------- driver ---
 template <class F>
 static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* map,
@@ -361,7 +335,7 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   const uint32_t nb = p.nbuckets();
   if (p.W > 64) return -1;
   if (p.n == 0) {
-    cudaMemsetAsync(out, 0, sizeof(XYZZ<F>), st);
+    cudaMemsetAsync(out, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
     return 0;
   }
   if ((uint64_t)p.n * p.W > s.cap_entries || nb > s.cap_buckets) return -2;
@@ -387,26 +361,16 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   k_accumulate<F><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb,
                                                                        p.task_log, partials);
   kstat_end(kind, st);
-  count_launch(reuse_sort ? 6 : 11);
+  count_launch(reuse_sort ? 5 : 10);
   k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, s.offsets, nb, p.task_log, buckets, s.heavy);
   k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, s.offsets, p.task_log, s.heavy, buckets);
-  const int nbits = p.W * p.c;  // <= 255 + c - 1 <= POW2_THREADS
   const int sbits = p.c - 1 - p.seg_log;  // bits of the segment index within a window
   const uint32_t nsegs = nb >> p.seg_log;
-  XYZZ<F>* V = reinterpret_cast<XYZZ<F>*>(s.winsum);
-  XYZZ<F>* tree = V + POW2_THREADS;
+  XYZZ<F>* V = out;  // MSM_VBITS entries
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
-  cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * POW2_THREADS, st);
+  cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
   k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
   k_segment_bits<F, BT><<<p.W * (1 + sbits), BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, V);
-  k_pow2_sum<F, false><<<1, POW2_THREADS, 0, st>>>(V, nbits, Fr::zero(), tree, out);
-  return cudaGetLastError() == cudaSuccess ? 0 : -3;
-}
-
-int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st) {
-  k_pow2_sum<Fq, true><<<1, POW2_THREADS, 0, st>>>(point, 256, k_mont,
-                                                   reinterpret_cast<G1XYZZ*>(s.winsum) + POW2_THREADS, out);
-  count_launch();
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -18,12 +18,13 @@
 //                      k_bucket_gather / k_bucket_heavy fold task partials into buckets
 //   5. k_bucket_segments / k_segment_bits   per-segment short running sums, then the segment
 //                      sums combined bit-wise into V[p] (weight 2^p)
-//   6. k_pow2_sum      sum_p 2^p V[p]: thread p doubles p times, then a tree
+//   6. (host)          sum_p 2^p V[p] by Horner on a CPU core: msm_horner_host
 // Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
 #pragma once
 #include <cuda_runtime.h>
 
 #include "ec.cuh"
+#include "host_fq.h"
 
 namespace fb {
 
@@ -31,6 +32,7 @@ constexpr int MSM_MIN_TASK_LOG = 4;
 constexpr uint32_t MSM_MIN_TASK = 1u << MSM_MIN_TASK_LOG;
 constexpr uint32_t MSM_HEAVY = 32;        // partials per bucket handled by one thread
 constexpr int MSM_HEAVY_THREADS = 128;
+constexpr int MSM_VBITS = 288;            // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
 
 struct MsmPlan {
   uint32_t n = 0;       // number of (scalar, base) pairs
@@ -65,13 +67,26 @@ struct MsmScratch {
 };
 
 // scalars: Montgomery Fr, addressed as scalars[map ? map[i] : i]; bases: affine Montgomery.
-// result: one XYZZ point on device (out).  Steps 1-3 are skipped when reuse_sort is set
-// (same scalars as the previous call on this scratch: B_g1 then B_g2).
+// result: out[MSM_VBITS] on device, the per-bit sums V[p] with  MSM = sum_p 2^p V[p]  (finish with
+// msm_horner_host after copying them to the host).  Steps 1-3 are skipped when reuse_sort is set
+// (same scalars as the previous call on this scratch: B_g2 then B_g1).
 int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
            MsmScratch& s, G1XYZZ* out, bool reuse_sort, cudaStream_t st);
-// out = k * point (one point), same parallel doubling tree; uses s.segS as scratch
-int scalar_mul_g1(const G1XYZZ* point, const Fr& k_mont, MsmScratch& s, G1XYZZ* out, cudaStream_t st);
 int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
            MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st);
+
+// Host side of step 6: Horner over the bit sums, on 64-bit-limb host arithmetic.
+template <class HF, class DF>
+inline XYZZ<HF> msm_horner_host(const XYZZ<DF>* V, int nbits) {
+  XYZZ<HF> acc = XYZZ<HF>::inf();
+  for (int p = nbits - 1; p >= 0; p--) {
+    if (!acc.is_inf()) acc = dbl(acc);
+    if (!V[p].is_inf()) {
+      XYZZ<HF> t{HF::from(V[p].x), HF::from(V[p].y), HF::from(V[p].zz), HF::from(V[p].zzz)};
+      acc = add(acc, t);
+    }
+  }
+  return acc;
+}
 
 }  // namespace fb
