@@ -4,7 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--log-rows 20] [--impl ours|reference]
 
 A step = one Groth16 prove of the synthetic circuit of SURVEY.md section 8(d) with
-2^log_rows rows (default 2^20 = BASELINE.json configs[2]; --log-rows 24 = configs[3]).
+2^log_rows rows (default 2^24 = BASELINE.json configs[3], the headline of north_star;
+--log-rows 20 = configs[2]).
   value  = seconds per prove with the witness already resident in HBM (fb_prove_device)
   e2e    = seconds per prove through the reference-facing call fb_prove with HOST buffers
            (pinned witness -> H2D inside the timed region, 256-byte proof read back)
@@ -381,10 +382,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log-rows", type=int, default=int(os.environ.get("FB_BENCH_LOG_ROWS", "20")))
-    ap.add_argument("--cpu-sample-log", type=int, default=18,
+    ap.add_argument("--log-rows", type=int, default=int(os.environ.get("FB_BENCH_LOG_ROWS", "24")),
+                    help="2^this rows: 24 = BASELINE.json configs[3] (default, the headline), 20 = configs[2]")
+    ap.add_argument("--cpu-sample-log", type=int, default=20,
                     help="CPU baseline proves 2^this rows (scaled) so the default run stays within minutes")
-    ap.add_argument("--ref-sample-log", type=int, default=17)
+    ap.add_argument("--ref-sample-log", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
