@@ -61,7 +61,7 @@ static void pk_release(ProvingKey* pk) {
   free_csr(pk->csr);
   pk->dom.destroy();
   cudaFree(pk->w);
-  for (int i = 0; i < 3; i++) cudaFree(pk->ev[i]);
+  for (int i = 0; i < 3; i++) { cudaFree(pk->ev[i]); cudaFree(pk->xtmp[i]); }
   cudaFree(pk->scratch);
   for (auto& x : pk->msm) x.release();
   cudaFree(pk->results);
@@ -117,6 +117,19 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     set_error("h query has %u points, need %llu", v.n_h, (unsigned long long)(m - 1));
     return FB_ERR_FORMAT;
   }
+  // distributed H pipeline: world = nshards = 2^g ranks with an NCCL exchange and a domain large enough
+  int dist_g = 0;
+  if (nshards > 1 && ctx->exchange && ctx->world == nshards && ctx->rank == shard && (nshards & (nshards - 1)) == 0) {
+    int g = 0;
+    while ((1 << g) < nshards) g++;
+    NttDomain probe;
+    probe.k = k;
+    const char* env = getenv("FB_DIST_NTT_MIN_LOG");
+    const int min_log = env ? atoi(env) : 20;
+    if (probe.dist_supported(g) && k >= min_log) dist_g = g;
+  }
+  pk->dist_g = dist_g;
+  const uint64_t ml = dist_g ? (m >> dist_g) : m;  // local length of the evaluation arrays
   cudaStream_t st = ctx->stream;
 #define PK_TRY(x) do { int _r = (x); if (_r) { pk_release(pk); return _r; } } while (0)
 #define PK_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); pk_release(pk); return FB_ERR_CUDA; } } while (0)
@@ -156,6 +169,10 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     rc = decode_g1_be(v.h, nh, tmp, checked, st);
     if (rc) { cudaFree(tmp); pk_release(pk); return rc; }
     slice(nh, lo, cnt);
+    if (dist_g) {  // H comes out of the distributed pipeline in block layout: positions [rank*ml, (rank+1)*ml)
+      lo = (uint64_t)shard * ml;
+      cnt = std::min<uint64_t>(ml, nh - lo);
+    }
     pk->len_h = (uint32_t)cnt;
     PK_CUDA(cudaMalloc(&pk->h, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
     if (cnt) k_gather_bitrev<<<(unsigned)std::min<uint64_t>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(
@@ -183,15 +200,37 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   PK_CUDA(cudaMemcpyAsync(pk->b_map, b_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice, st));
   PK_CUDA(cudaStreamSynchronize(st));
   // CSR + domain + workspaces
-  PK_TRY(upload_csr(csr, pk->csr, st));
+  if (dist_g) {
+    HostCsr sub;
+    const uint32_t G = 1u << dist_g;
+    for (int mi = 0; mi < 3; mi++) sub.rowptr[mi].push_back(0);
+    for (uint32_t row = shard; row < csr.n_gates; row += G) {
+      for (int mi = 0; mi < 3; mi++) {
+        for (uint32_t q = csr.rowptr[mi][row]; q < csr.rowptr[mi][row + 1]; q++) {
+          sub.col[mi].push_back(csr.col[mi][q]);
+          sub.cidx[mi].push_back(csr.cidx[mi][q]);
+        }
+        sub.rowptr[mi].push_back((uint32_t)sub.col[mi].size());
+      }
+      sub.n_gates++;
+    }
+    sub.coef = csr.coef;
+    PK_TRY(upload_csr(sub, pk->csr, st));
+    pk->n_gates_global = csr.n_gates;
+  } else {
+    PK_TRY(upload_csr(csr, pk->csr, st));
+    pk->n_gates_global = csr.n_gates;
+  }
   if (pk->dom.init(k, st) != 0) {
     set_error("NTT domain init failed: %s", cudaGetErrorString(cudaGetLastError()));
     pk_release(pk);
     return FB_ERR_CUDA;
   }
   PK_CUDA(cudaMalloc(&pk->w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr)));
-  for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->ev[i], m * sizeof(Fr)));
-  PK_CUDA(cudaMalloc(&pk->scratch, m * sizeof(Fr)));
+  for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->ev[i], ml * sizeof(Fr)));
+  PK_CUDA(cudaMalloc(&pk->scratch, ml * sizeof(Fr)));
+  if (dist_g)
+    for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->xtmp[i], ml * sizeof(Fr)));
   uint64_t l_lo, l_cnt;
   slice(v.n_l, l_lo, l_cnt);
   pk->plan_h = MsmPlan::make(pk->len_h);
@@ -325,20 +364,32 @@ static int prove_launch(ProvingKey* pk, uint64_t* h_out) {
   if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)vslot(pk->results, 1), false, sL);
   if (!rc) FB_CUDA(fetch(1, sizeof(G1XYZZ) * MSM_VBITS, sL, 1));
   // R1CS evaluation and the H pipeline on the main stream
-  if (!rc) rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
   if (rc) {
-    if (rc != FB_ERR_CUDA) set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
     return FB_ERR_CUDA;
   }
-  cudaEventRecord(T.ev[2], st);
-  for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(pk->ev[i], st);
-  pk->dom.pointwise_then_icoset_fft(pk->ev[0], pk->ev[1], pk->ev[2], st);
+  if (pk->dist_g) {
+    if (h_out) { set_error("h_out is not available on a distributed key"); return FB_ERR_ARG; }
+    rc = eval_r1cs_cyclic(pk->csr, pk->w, pk->n_in, pk->n_gates_global, pk->dist_g, pk->shard, pk->ev[0], pk->ev[1],
+                          pk->ev[2], m >> pk->dist_g, st);
+    if (rc) return rc;
+    cudaEventRecord(T.ev[2], st);
+    rc = pk->dom.dist_h_pipeline(pk->ev, pk->xtmp, pk->dist_g, pk->shard, dist_exchange(ctx), st);
+    if (rc) { if (rc != FB_ERR_CUDA) set_error("distributed H pipeline failed (%d)", rc); return FB_ERR_CUDA; }
+  } else {
+    rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
+    if (rc) return rc;
+    cudaEventRecord(T.ev[2], st);
+    for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(pk->ev[i], st);
+    pk->dom.pointwise_then_icoset_fft(pk->ev[0], pk->ev[1], pk->ev[2], st);
+  }
   cudaEventRecord(T.ev[3], st);
   if (h_out) {
     pk->dom.bitrev(pk->scratch, pk->ev[0], st);
     FB_CUDA(cudaMemcpyAsync(h_out, pk->scratch, (m - 1) * sizeof(Fr), cudaMemcpyDeviceToHost, st));
   }
-  rc = msm_g1(pk->h, pk->ev[0] + h_lo, nullptr, pk->plan_h, pk->msm[0], (G1XYZZ*)vslot(pk->results, 0), false, st);
+  rc = msm_g1(pk->h, pk->ev[0] + (pk->dist_g ? 0 : h_lo), nullptr, pk->plan_h, pk->msm[0],
+              (G1XYZZ*)vslot(pk->results, 0), false, st);
   if (rc) { set_error("MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
   FB_CUDA(fetch(0, sizeof(G1XYZZ) * MSM_VBITS, st, 0));
   cudaEventRecord(T.ev[4], st);

@@ -1,0 +1,206 @@
+// Multi-GPU plumbing of the distributed H pipeline: the all-to-all between the cyclic and block
+// layouts of ntt.cu, over NCCL (NVLink / NVSwitch) with one process per GPU.
+//
+// The reference has no distributed path at all (single process); this is
+// north_star subsystem (3): "the four-step transpose sharded across GPUs via NCCL all-to-all".
+// libnccl is bound at run time (dlopen) so the library still loads on a machine without it; the
+// host application creates the unique id on rank 0, ships it to the other ranks by any means
+// (bench.py: torch.distributed broadcast) and every rank calls fb_dist_init.
+#include <dlfcn.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
+#include "internal.h"
+
+namespace fb {
+
+// ---- the slice of the NCCL API we use (types restated from nccl.h) ----
+typedef void* ncclComm_t;
+struct ncclUniqueId_ { char internal[128]; };
+static const int kNcclUint8 = 1;  // ncclDataType_t::ncclUint8
+struct NcclApi {
+  int (*GetUniqueId)(ncclUniqueId_*);
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_, int);
+  int (*CommDestroy)(ncclComm_t);
+  int (*GroupStart)();
+  int (*GroupEnd)();
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(int);
+  bool ok = false;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) {
+      api.GetUniqueId = (int (*)(ncclUniqueId_*))dlsym(lib, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId_, int))dlsym(lib, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(ncclComm_t))dlsym(lib, "ncclCommDestroy");
+      api.GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+      api.GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+      api.Send = (int (*)(const void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclSend");
+      api.Recv = (int (*)(void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclRecv");
+      api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+    }
+  }
+  return api;
+}
+
+struct NcclExchange : NttExchange {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count, cudaStream_t st) override {
+    NcclApi& n = nccl();
+    int rc = n.GroupStart();
+    const size_t bytes = count * sizeof(Fr);
+    for (int v = 0; v < narrays && !rc; v++)
+      for (int r = 0; r < world && !rc; r++) {
+        rc = n.Send(send[v] + (uint64_t)r * count, bytes, kNcclUint8, r, comm, st);
+        if (!rc) rc = n.Recv(recv[v] + (uint64_t)r * count, bytes, kNcclUint8, r, comm, st);
+      }
+    int rc2 = n.GroupEnd();
+    if (rc || rc2) {
+      set_error("NCCL all-to-all failed: %s", n.GetErrorString ? n.GetErrorString(rc ? rc : rc2) : "?");
+      return FB_ERR_CUDA;
+    }
+    count_launch(1);
+    return 0;
+  }
+};
+
+NttExchange* dist_exchange(Ctx* ctx) { return reinterpret_cast<NttExchange*>(ctx->exchange); }
+
+// ---- single-process stand-in used by the one-GPU test: G host threads, one per virtual rank ----
+struct LocalWorld {
+  int world;
+  std::mutex mu;
+  std::condition_variable cv;
+  int waiting = 0;
+  uint64_t generation = 0;
+  std::vector<const Fr* const*> send;
+  explicit LocalWorld(int w) : world(w), send(w) {}
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    uint64_t gen = generation;
+    if (++waiting == world) { waiting = 0; generation++; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  }
+};
+struct LocalExchange : NttExchange {
+  LocalWorld* w;
+  int rank;
+  int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count, cudaStream_t st) override {
+    cudaStreamSynchronize(st);          // my send buffers are final
+    w->send[rank] = send;
+    w->barrier();                       // everybody's are
+    for (int v = 0; v < narrays; v++)
+      for (int r = 0; r < w->world; r++)
+        cudaMemcpyAsync(recv[v] + (uint64_t)r * count, w->send[r][v] + (uint64_t)rank * count, count * sizeof(Fr),
+                        cudaMemcpyDeviceToDevice, st);
+    cudaStreamSynchronize(st);
+    w->barrier();                       // nobody overwrites a send buffer that is still being read
+    return 0;
+  }
+};
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int fb_dist_unique_id(uint8_t id[128]) {
+  if (!id) return FB_ERR_ARG;
+  NcclApi& n = nccl();
+  if (!n.ok) { set_error("libnccl.so.2 not available"); return FB_ERR_CUDA; }
+  ncclUniqueId_ u;
+  int rc = n.GetUniqueId(&u);
+  if (rc) { set_error("ncclGetUniqueId: %s", n.GetErrorString(rc)); return FB_ERR_CUDA; }
+  memcpy(id, u.internal, 128);
+  return FB_OK;
+}
+
+int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) { set_error("fb_dist_init: bad argument"); return FB_ERR_ARG; }
+  NcclApi& n = nccl();
+  if (!n.ok) { set_error("libnccl.so.2 not available"); return FB_ERR_CUDA; }
+  FB_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId_ u;
+  memcpy(u.internal, id, 128);
+  NcclExchange* x = new NcclExchange();
+  x->rank = rank;
+  x->world = world;
+  int rc = n.CommInitRank(&x->comm, world, u, rank);
+  if (rc) { set_error("ncclCommInitRank: %s", n.GetErrorString(rc)); delete x; return FB_ERR_CUDA; }
+  ctx->exchange = x;
+  ctx->rank = rank;
+  ctx->world = world;
+  return FB_OK;
+}
+
+// One-GPU check of the distributed H pipeline: 2^g virtual ranks (host threads, own streams) with the
+// exchange done by device-to-device copies.  a, b, c: row evaluations [2^log_n][4]; out: H
+// coefficients [2^log_n - 1][4] in natural order.
+int fb_test_dist_h(fb_ctx* ctx_, int log_n, int g, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                   uint64_t* out) {
+  Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
+  if (!ctx || !a || !b || !c || !out) return FB_ERR_ARG;
+  FB_CUDA(cudaSetDevice(ctx->device));
+  NttDomain dom;
+  if (dom.init(log_n, ctx->stream) != 0) { set_error("domain init failed"); return FB_ERR_DOMAIN; }
+  FB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (!dom.dist_supported(g)) { dom.destroy(); set_error("2^%d over 2^%d ranks is not supported", log_n, g); return FB_ERR_ARG; }
+  const int G = 1 << g, kl = log_n - g;
+  const uint64_t m = 1ull << log_n, ml = 1ull << kl;
+  LocalWorld world(G);
+  std::vector<std::thread> th;
+  std::vector<int> rcs(G, 0);
+  std::vector<Fr> result(m);
+  const uint64_t* src[3] = {a, b, c};
+  for (int r = 0; r < G; r++) {
+    th.emplace_back([&, r] {
+      cudaSetDevice(ctx->device);
+      cudaStream_t st;
+      cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+      Fr *ev[3], *tmp[3];
+      std::vector<Fr> host(ml);
+      for (int v = 0; v < 3; v++) {
+        cudaMalloc(&ev[v], ml * sizeof(Fr));
+        cudaMalloc(&tmp[v], ml * sizeof(Fr));
+        for (uint64_t j = 0; j < ml; j++) memcpy(&host[j], src[v] + 4 * ((j << g) | (uint64_t)r), 32);  // cyclic
+        cudaMemcpyAsync(ev[v], host.data(), ml * sizeof(Fr), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+      }
+      LocalExchange x;
+      x.w = &world;
+      x.rank = r;
+      rcs[r] = dom.dist_h_pipeline(ev, tmp, g, r, &x, st);
+      cudaStreamSynchronize(st);
+      if (cudaGetLastError() != cudaSuccess) rcs[r] = -9;
+      // block layout, bit-reversed coefficient order: global position r * ml + j
+      cudaMemcpy(result.data() + (uint64_t)r * ml, ev[0], ml * sizeof(Fr), cudaMemcpyDeviceToHost);
+      for (int v = 0; v < 3; v++) { cudaFree(ev[v]); cudaFree(tmp[v]); }
+      cudaStreamDestroy(st);
+    });
+  }
+  for (auto& t : th) t.join();
+  dom.destroy();
+  for (int r = 0; r < G; r++)
+    if (rcs[r]) { set_error("virtual rank %d failed (%d)", r, rcs[r]); return FB_ERR_CUDA; }
+  for (uint64_t p = 0; p < m; p++) {
+    uint64_t i = 0;
+    for (int bit = 0; bit < log_n; bit++) i |= ((p >> bit) & 1) << (log_n - 1 - bit);
+    if (i < m - 1) memcpy(out + 4 * i, &result[p], 32);
+  }
+  return FB_OK;
+}
+
+}  // extern "C"

@@ -56,6 +56,9 @@ struct Ctx {
   cudaStream_t stream = nullptr;   // R1CS eval, H pipeline, H MSM, copies
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // L / A / B MSMs run beside the H pipeline
   cudaEvent_t aux_done[3] = {nullptr, nullptr, nullptr};
+  // multi-GPU (fb_dist_init): rank / world of this process and the NTT exchange transport
+  int rank = 0, world = 1;
+  void* exchange = nullptr;  // NttExchange*
 };
 
 struct ProvingKey {
@@ -88,6 +91,11 @@ struct ProvingKey {
   void* results_host = nullptr;  // pinned
   // base-index shard handled by this key (multi-GPU): fractions [shard, shard+1)/nshards
   int shard = 0, nshards = 1;
+  // distributed H pipeline (0 = evaluation + H replicated on every rank): R1CS rows are dealt
+  // cyclically over 2^dist_g ranks, ev[] are local arrays of m >> dist_g, xtmp the exchange buffers
+  int dist_g = 0;
+  uint32_t n_gates_global = 0;
+  Fr* xtmp[3] = {nullptr, nullptr, nullptr};
 };
 
 struct Circuit {
@@ -115,8 +123,14 @@ int host_decode_g2(const uint8_t* be, G2Affine& out);
 void host_encode_g1(const G1Affine& p, uint8_t* be);
 void host_encode_g2(const G2Affine& p, uint8_t* be);
 
+// dist.cu
+struct NttExchange;
+NttExchange* dist_exchange(Ctx* ctx);
+
 // prove.cu
 int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,
               cudaStream_t st);
+int eval_r1cs_cyclic(const DevCsr& local_csr, const Fr* w, uint32_t n_in, uint32_t n_gates_global, int g, int rank,
+                     Fr* a, Fr* b, Fr* c, uint64_t ml, cudaStream_t st);
 
 }  // namespace fb

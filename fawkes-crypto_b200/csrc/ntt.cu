@@ -105,20 +105,23 @@ __device__ __forceinline__ Fr twiddle(const Fr* tab, int k, int t, uint32_t j) {
 }
 
 // DIF stages over the tile's b "mid" bits (largest half first)
+// k: log2 of the GLOBAL transform (twiddle tables); lb: bit position of the tile's mid bits in the
+// LOCAL array; sh: distributed layout, global index = (local << sh.shift) | sh.low (shift = 0 on one GPU)
+struct NttShard { int shift; uint32_t low; };
 template <bool NEGINV>
 __device__ __forceinline__ void dif_stages(const Tile& s, const Fr* tab, int k, int lb, int a,
-                                           int b, uint32_t lo0) {
+                                           int b, uint32_t lo0, NttShard sh) {
   const int nb = 1 << (a + b - 1);
   for (int d = 0; d < b; d++) {
     const int hm = 1 << (b - 1 - d);
-    const int t = k - lb - b + d;
+    const int t = k - (lb + sh.shift) - b + d;
     for (int q = threadIdx.x; q < nb; q += blockDim.x) {
       const int l = q & ((1 << a) - 1);
       const int qm = q >> a;
       const int jm = qm & (hm - 1);
       const int mid = ((qm - jm) << 1) + jm;
       const int i0 = (mid << a) + l, i1 = ((mid + hm) << a) + l;
-      const uint32_t j = ((uint32_t)jm << lb) + lo0 + l;
+      const uint32_t j = ((((uint32_t)jm << lb) + lo0 + l) << sh.shift) | sh.low;
       Fr w = twiddle<NEGINV>(tab, k, t, j);
       Fr u = s.get(i0), v = s.get(i1);
       s.put(i0, add(u, v));
@@ -130,18 +133,18 @@ __device__ __forceinline__ void dif_stages(const Tile& s, const Fr* tab, int k, 
 // DIT stages over the tile's b "mid" bits (smallest half first)
 template <bool NEGINV>
 __device__ __forceinline__ void dit_stages(const Tile& s, const Fr* tab, int k, int lb, int a,
-                                           int b, uint32_t lo0) {
+                                           int b, uint32_t lo0, NttShard sh) {
   const int nb = 1 << (a + b - 1);
   for (int d = 0; d < b; d++) {
     const int hm = 1 << d;
-    const int t = k - 1 - (lb + d);
+    const int t = k - 1 - (lb + sh.shift + d);
     for (int q = threadIdx.x; q < nb; q += blockDim.x) {
       const int l = q & ((1 << a) - 1);
       const int qm = q >> a;
       const int jm = qm & (hm - 1);
       const int mid = ((qm - jm) << 1) + jm;
       const int i0 = (mid << a) + l, i1 = ((mid + hm) << a) + l;
-      const uint32_t j = ((uint32_t)jm << lb) + lo0 + l;
+      const uint32_t j = ((((uint32_t)jm << lb) + lo0 + l) << sh.shift) | sh.low;
       Fr w = twiddle<NEGINV>(tab, k, t, j);
       Fr u = s.get(i0), v = mul(s.get(i1), w);
       s.put(i0, add(u, v));
@@ -158,7 +161,7 @@ __device__ __forceinline__ void dit_stages(const Tile& s, const Fr* tab, int k, 
 template <int MODE, bool NEG0>
 __global__ void __launch_bounds__(NTT_THREADS)
 k_ntt_pass(Fr* x, const Fr* y, const Fr* z, const Fr* tab0, const Fr* tab1, int k, int lb, int a,
-           int b, Fr k1, Fr k2) {
+           int b, Fr k1, Fr k2, NttShard sh) {
   extern __shared__ uint4 smem[];
   Tile s{smem, smem + (1 << (a + b))};
   const int tile = 1 << (a + b);
@@ -178,11 +181,11 @@ k_ntt_pass(Fr* x, const Fr* y, const Fr* z, const Fr* tab0, const Fr* tab1, int 
     s.put(e, v);
   }
   __syncthreads();
-  if (MODE == 0 || MODE == 3) dif_stages<NEG0>(s, tab0, k, lb, a, b, lo0);
-  if (MODE == 1) dit_stages<NEG0>(s, tab0, k, lb, a, b, lo0);
+  if (MODE == 0 || MODE == 3) dif_stages<NEG0>(s, tab0, k, lb, a, b, lo0, sh);
+  if (MODE == 1) dit_stages<NEG0>(s, tab0, k, lb, a, b, lo0, sh);
   if (MODE == 2) {
-    dif_stages<true>(s, tab0, k, lb, a, b, lo0);
-    dit_stages<false>(s, tab1, k, lb, a, b, lo0);
+    dif_stages<true>(s, tab0, k, lb, a, b, lo0, sh);
+    dit_stages<false>(s, tab1, k, lb, a, b, lo0, sh);
   }
   for (int e = threadIdx.x; e < tile; e += blockDim.x) {
     const int l = e & ((1 << a) - 1), mid = e >> a;
@@ -283,14 +286,17 @@ void NttDomain::destroy() {
   tab_plain = tab_coset = tab_icoset = nullptr;
 }
 
+// kl = log2 of the local array length (= k on one GPU)
 template <int MODE, bool NEG0>
 static void launch_pass(Fr* x, const Fr* y, const Fr* z, const Fr* t0, const Fr* t1, int k, int lb,
-                        int b, const Fr& k1, const Fr& k2, cudaStream_t st) {
+                        int b, const Fr& k1, const Fr& k2, cudaStream_t st, int kl = -1,
+                        NttShard sh = NttShard{0, 0}) {
+  if (kl < 0) kl = k;
   int a = std::min(lb, NTT_LOG_TILE - b);
   size_t sm = (size_t)sizeof(Fr) << (a + b);
-  unsigned blocks = 1u << (k - a - b);
+  unsigned blocks = 1u << (kl - a - b);
   kstat_begin(KSTAT_NTT, st);
-  k_ntt_pass<MODE, NEG0><<<blocks, NTT_THREADS, sm, st>>>(x, y, z, t0, t1, k, lb, a, b, k1, k2);
+  k_ntt_pass<MODE, NEG0><<<blocks, NTT_THREADS, sm, st>>>(x, y, z, t0, t1, k, lb, a, b, k1, k2, sh);
   kstat_end(KSTAT_NTT, st);
   count_launch();
 }
@@ -348,6 +354,100 @@ void NttDomain::transform(Fr* x, Fr* scratch, int kind, cudaStream_t st) const {
     k_bitrev_permute<<<pb, 256, 0, st>>>(scratch, x, k);
     cudaMemcpyAsync(x, scratch, sizeof(Fr) << k, cudaMemcpyDeviceToDevice, st);
   }
+}
+
+// ------------------------------------------------------------ distributed ---
+// G = 2^g ranks.  "cyclic" layout: rank r holds the elements with global index = r (mod G), local
+// index = global >> g; every butterfly on global bits >= g is local.  "block" layout: rank r holds the
+// contiguous range [r * m/G, (r+1) * m/G); every butterfly on global bits < k - g is local.
+// ifft + coset_fft:  cyclic DIF on bits [bm, k)  -> exchange ->  block mid pass on bits [0, bm)
+//                    -> exchange ->  cyclic DIT on bits [bm, k).          (bm = 12, g <= bm <= k - g)
+// final:             cyclic pointwise + DIF on bits [bm, k) -> exchange -> block DIF on bits [0, bm):
+//                    H comes out bit-reversed in block layout = the rank's contiguous H-base shard.
+// One exchange = an all-to-all of m/G elements per rank; a, b, c travel in one grouped call.
+__global__ void k_unpack_to_block(Fr* __restrict__ dst, const Fr* __restrict__ src, int g, uint64_t C) {
+  // src[r * C + q] (chunk received from rank r)  ->  dst[q * G + r]
+  const uint64_t n = C << g;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t q = i >> g, r = i & ((1u << g) - 1);
+    st_fr(dst + i, ld_fr(src + r * C + q));
+  }
+}
+__global__ void k_pack_from_block(Fr* __restrict__ dst, const Fr* __restrict__ src, int g, uint64_t C) {
+  // src[q * G + r]  ->  dst[r * C + q] (chunk to send to rank r)
+  const uint64_t n = C << g;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t q = i >> g, r = i & ((1u << g) - 1);
+    st_fr(dst + r * C + q, ld_fr(src + i));
+  }
+}
+
+bool NttDomain::dist_supported(int g) const {
+  return g >= 1 && k > NTT_LOG_TILE && k - g >= NTT_LOG_TILE && NTT_LOG_TILE - g >= NTT_MIN_LO;
+}
+
+void NttDomain::dist_plan(int g, int* n_pass, int* lb, int* b) const {
+  // strided cyclic passes over global bits [bm, k) = local bits [bm - g, k - g)
+  const int bm = NTT_LOG_TILE, rem = k - bm, maxb = NTT_LOG_TILE - NTT_MIN_LO;
+  const int np = (rem + maxb - 1) / maxb;
+  int pos = bm - g;
+  for (int i = 0; i < np; i++) {
+    b[i] = rem / np + (i < rem % np ? 1 : 0);
+    lb[i] = pos;
+    pos += b[i];
+  }
+  *n_pass = np;
+}
+
+static unsigned grid_for(uint64_t n) { return (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 16); }
+
+int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int rank, NttExchange* xch,
+                               cudaStream_t st) const {
+  const int kl = k - g, bm = NTT_LOG_TILE;
+  const uint64_t ml = 1ull << kl, C = ml >> g;
+  int np, lb[8], b[8];
+  dist_plan(g, &np, lb, b);
+  const NttShard cyc{g, (uint32_t)rank}, blk{0, 0};
+  Fr z = Fr::zero();
+  // 1. cyclic inverse DIF on the high bits (three arrays)
+  for (int v = 0; v < 3; v++)
+    for (int i = np - 1; i >= 0; i--)
+      launch_pass<0, true>(ev[v], nullptr, nullptr, tab_plain, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+  // 2. cyclic -> block: contiguous chunks out, strided placement in
+  const Fr* send3[3] = {ev[0], ev[1], ev[2]};
+  int rc = xch->all_to_all(send3, tmp, 3, C, st);
+  if (rc) return rc;
+  for (int v = 0; v < 3; v++) k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[v], tmp[v], g, C);
+  // 3. block layout: last bm inverse stages + first bm forward (coset) stages in one tile
+  for (int v = 0; v < 3; v++)
+    launch_pass<2, true>(ev[v], nullptr, nullptr, tab_plain, tab_coset, k, 0, bm, z, z, st, kl, blk);
+  // 4. block -> cyclic
+  for (int v = 0; v < 3; v++) k_pack_from_block<<<grid_for(ml), 256, 0, st>>>(tmp[v], ev[v], g, C);
+  const Fr* send3b[3] = {tmp[0], tmp[1], tmp[2]};
+  rc = xch->all_to_all(send3b, ev, 3, C, st);
+  if (rc) return rc;
+  // 5. cyclic forward (coset) DIT on the high bits
+  for (int v = 0; v < 3; v++)
+    for (int i = 0; i < np; i++)
+      launch_pass<1, false>(ev[v], nullptr, nullptr, tab_coset, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+  // 6. pointwise + cyclic inverse-coset DIF on the high bits
+  for (int i = np - 1; i >= 0; i--) {
+    if (i == np - 1)
+      launch_pass<3, false>(ev[0], ev[1], ev[2], tab_icoset, nullptr, k, lb[i], b[i], k1, k2, st, kl, cyc);
+    else
+      launch_pass<0, false>(ev[0], nullptr, nullptr, tab_icoset, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+  }
+  // 7. cyclic -> block, then the low bm stages: H in bit-reversed order, block layout
+  const Fr* send1[1] = {ev[0]};
+  Fr* recv1[1] = {tmp[0]};
+  rc = xch->all_to_all(send1, recv1, 1, C, st);
+  if (rc) return rc;
+  k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[0], tmp[0], g, C);
+  launch_pass<0, false>(ev[0], nullptr, nullptr, tab_icoset, nullptr, k, 0, bm, z, z, st, kl, blk);
+  count_launch(10);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 void NttDomain::bitrev(Fr* dst, const Fr* src, cudaStream_t st) const {

@@ -12,6 +12,14 @@ constexpr int NTT_LOG_TILE = 12;   // 4096 elements = 128 KiB of shared memory p
 constexpr int NTT_MIN_LO = 3;      // strided passes move >= 8 consecutive elements (256 B)
 constexpr int NTT_THREADS = 512;
 
+// Transport of the distributed transform: every rank sends chunk r (count elements) of each of
+// `narrays` send buffers to rank r and receives chunk r of each recv buffer from rank r.
+struct NttExchange {
+  virtual ~NttExchange() {}
+  virtual int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count,
+                         cudaStream_t st) = 0;
+};
+
 struct NttDomain {
   int k = 0;
   Fr omega, minv, k1, k2;
@@ -28,6 +36,11 @@ struct NttDomain {
   void pointwise_then_icoset_fft(Fr* a, const Fr* b, const Fr* c, cudaStream_t st) const;
   void transform(Fr* x, Fr* scratch, int kind, cudaStream_t st) const;
   void bitrev(Fr* dst, const Fr* src, cudaStream_t st) const;
+  // distributed H pipeline over G = 2^g ranks (see ntt.cu); ev/tmp are local arrays of 2^(k-g)
+  bool dist_supported(int g) const;
+  void dist_plan(int g, int* n_pass, int* lb, int* b) const;
+  int dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int rank, NttExchange* xch,
+                      cudaStream_t st) const;
 };
 
 }  // namespace fb

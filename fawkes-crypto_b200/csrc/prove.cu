@@ -54,4 +54,27 @@ int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c
   return FB_OK;
 }
 
+// Distributed variant: this rank holds the rows i = rank (mod 2^g) (local row j <-> global row
+// j * 2^g + rank), the layout the distributed H pipeline starts from.
+int eval_r1cs_cyclic(const DevCsr& csr, const Fr* w, uint32_t n_in, uint32_t n_gates_global, int g, int rank,
+                     Fr* a, Fr* b, Fr* c, uint64_t ml, cudaStream_t st) {
+  const uint32_t ng = csr.n_gates;  // local rows
+  Fr* outs[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    FB_CUDA(cudaMemsetAsync(outs[i] + ng, 0, (ml - ng) * sizeof(Fr), st));
+    if (ng) {
+      unsigned blocks = (unsigned)std::min<uint64_t>((ng + 127) / 128, 148 * 32);
+      k_spmv<<<blocks, 128, 0, st>>>(csr.rowptr[i], csr.col[i], csr.cidx[i], csr.coef, w, outs[i], ng);
+      count_launch();
+    }
+  }
+  // bellman's `input_i * 0 = 0` rows: global row n_gates + i
+  for (uint32_t i = 0; i < n_in; i++) {
+    const uint64_t row = (uint64_t)n_gates_global + i;
+    if ((int)(row & ((1u << g) - 1)) == rank)
+      FB_CUDA(cudaMemcpyAsync(a + (row >> g), w + i, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+  }
+  return FB_OK;
+}
+
 }  // namespace fb

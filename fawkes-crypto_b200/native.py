@@ -68,6 +68,9 @@ SIGNATURES = {
     "fb_test_field": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, C.c_uint64]),
     "fb_test_ntt": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_test_h": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, f32p]),
+    "fb_test_dist_h": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "fb_dist_unique_id": (C.c_int, [vp]),
+    "fb_dist_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_test_msm": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp, C.c_int, f32p]),
     "fb_test_fixed_base": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp]),
     "fb_probe_imad": (C.c_int, [vp, C.POINTER(C.c_double)]),

@@ -122,6 +122,14 @@ int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* pa
  * [0] h2d  [1] r1cs eval  [2] H pipeline (7 NTTs)  [3] MSMs  [4] d2h+assembly (host)  [5] total */
 int fb_prove_timings(const fb_pk* pk, float ms[6]);
 
+/* ---- multi-GPU (one process per GPU) ----------------------------------------------------
+ * fb_dist_unique_id on rank 0 (NCCL unique id, 128 bytes), ship it to every rank, then fb_dist_init on
+ * each.  A key loaded afterwards with fb_pk_load_shard(shard = rank, nshards = world) also shards the
+ * R1CS rows and the H pipeline (four-step NTT, NCCL all-to-all over NVLink) when world is a power of
+ * two and the domain is large enough; otherwise those stay replicated and only the MSMs shard. */
+int fb_dist_unique_id(uint8_t id[128]);
+int fb_dist_init(fb_ctx* ctx, int rank, int world, const uint8_t id[128]);
+
 /* ---- setup / verify ---------------------------------------------------------- */
 /* trapdoor = alpha, beta, gamma, delta, tau (Num<Fr>); generators = the standard BN254
  * ones.  Writes bellman-format Parameters bytes (free with fb_free). */
@@ -159,6 +167,10 @@ int fb_test_ntt(fb_ctx* ctx, int log_n, int kind, uint64_t* data);
 /* H coefficients from row evaluations a,b,c (each [2^log_n][4]); out [2^log_n - 1][4] */
 int fb_test_h(fb_ctx* ctx, int log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c,
               uint64_t* out, float* ms);
+/* distributed H pipeline on ONE GPU: 2^g virtual ranks, exchange by device copies (test of the
+ * cyclic/block layouts and kernels without NCCL); out = H coefficients [2^log_n - 1][4] */
+int fb_test_dist_h(fb_ctx* ctx, int log_n, int g, const uint64_t* a, const uint64_t* b, const uint64_t* c,
+                   uint64_t* out);
 /* MSM on host buffers: group 1 (bases 64 B) or 2 (128 B); result raw affine; reps>1 times it */
 int fb_test_msm(fb_ctx* ctx, int group, const uint8_t* bases_raw, const uint64_t* scalars,
                 uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep);

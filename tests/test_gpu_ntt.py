@@ -61,3 +61,24 @@ def test_roundtrip_large(ctx):
         assert not np.array_equal(x, y)
         fb.native.check(fb.native.lib.fb_test_ntt(ctx.handle, log_n, inv, y.ctypes.data))
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("log_n,g", [(16, 1), (17, 2), (18, 3), (16, 3)])
+def test_distributed_h_pipeline_layouts(ctx, log_n, g):
+    """Four-step (cyclic/block) H pipeline with 2^g virtual ranks on one GPU == the single-GPU pipeline
+    (itself checked against the oracle above).  The NCCL transport is exercised by bench.py --gpus N."""
+    import fawkes_crypto_b200 as fb
+    rng = np.random.default_rng(log_n * 10 + g)
+    n = 1 << log_n
+    arrs = []
+    for _ in range(3):
+        x = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+        x[:, 3] &= np.uint64((1 << 60) - 1)
+        arrs.append(x)
+    ref = np.zeros((n - 1, 4), dtype=np.uint64)
+    fb.native.check(fb.native.lib.fb_test_h(ctx.handle, log_n, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                            arrs[2].ctypes.data, ref.ctypes.data, None))
+    out = np.zeros((n - 1, 4), dtype=np.uint64)
+    fb.native.check(fb.native.lib.fb_test_dist_h(ctx.handle, log_n, g, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                                 arrs[2].ctypes.data, out.ctypes.data))
+    assert np.array_equal(out, ref)
