@@ -226,7 +226,8 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     pk_release(pk);
     return FB_ERR_CUDA;
   }
-  PK_CUDA(cudaMalloc(&pk->w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr)));
+  // padded to a multiple of the world size so the witness can be all-gathered in equal chunks
+  PK_CUDA(cudaMalloc(&pk->w, ((size_t)(pk->n_in + pk->n_aux) + (size_t)nshards) * sizeof(Fr)));
   for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->ev[i], ml * sizeof(Fr)));
   PK_CUDA(cudaMalloc(&pk->scratch, ml * sizeof(Fr)));
   if (dist_g)
@@ -425,6 +426,20 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
   if (dev_w) {
     FB_CUDA(cudaMemcpyAsync(pk->w, dev_w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr),
                             cudaMemcpyDeviceToDevice, st));
+  } else if (ctx->exchange && ctx->world == pk->nshards && pk->nshards > 1 && ctx->rank == pk->shard) {
+    // every rank uploads 1/world of the witness over its own PCIe link, NVLink all-gathers the rest
+    const uint64_t total = (uint64_t)n_in + n_aux, W = pk->nshards;
+    const uint64_t chunk = (total + W - 1) / W;
+    const uint64_t lo = chunk * pk->shard, hi = std::min(total, lo + chunk);
+    for (uint64_t pos = lo; pos < hi;) {  // [lo, hi) may straddle the inputs | aux boundary
+      const bool in_inputs = pos < n_in;
+      const uint64_t seg_end = in_inputs ? std::min<uint64_t>(hi, n_in) : hi;
+      const uint64_t* src = in_inputs ? inputs + 4 * pos : aux + 4 * (pos - n_in);
+      FB_CUDA(cudaMemcpyAsync(pk->w + pos, src, (seg_end - pos) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      pos = seg_end;
+    }
+    int grc = dist_all_gather_inplace(ctx, pk->w, chunk * sizeof(Fr), st);
+    if (grc) return grc;
   } else {
     FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));

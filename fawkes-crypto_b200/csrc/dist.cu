@@ -28,6 +28,7 @@ struct NcclApi {
   int (*GroupEnd)();
   int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(int);
   bool ok = false;
 };
@@ -46,6 +47,7 @@ static NcclApi& nccl() {
       api.GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
       api.Send = (int (*)(const void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclSend");
       api.Recv = (int (*)(void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclRecv");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(lib, "ncclAllGather");
       api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
       api.ok = api.GetUniqueId && api.CommInitRank && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
     }
@@ -76,6 +78,17 @@ struct NcclExchange : NttExchange {
 };
 
 NttExchange* dist_exchange(Ctx* ctx) { return reinterpret_cast<NttExchange*>(ctx->exchange); }
+
+// In-place all-gather of equal chunks over NVLink: rank r has filled buf[r*chunk_bytes ..) already.
+int dist_all_gather_inplace(Ctx* ctx, void* buf, size_t chunk_bytes, cudaStream_t st) {
+  NcclExchange* x = reinterpret_cast<NcclExchange*>(ctx->exchange);
+  NcclApi& n = nccl();
+  if (!x || !n.AllGather) { set_error("NCCL all-gather unavailable"); return FB_ERR_CUDA; }
+  int rc = n.AllGather((const uint8_t*)buf + (size_t)x->rank * chunk_bytes, buf, chunk_bytes, kNcclUint8, x->comm, st);
+  if (rc) { set_error("ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(rc) : "?"); return FB_ERR_CUDA; }
+  count_launch(1);
+  return 0;
+}
 
 // ---- single-process stand-in used by the one-GPU test: G host threads, one per virtual rank ----
 struct LocalWorld {

@@ -126,6 +126,7 @@ void host_encode_g2(const G2Affine& p, uint8_t* be);
 // dist.cu
 struct NttExchange;
 NttExchange* dist_exchange(Ctx* ctx);
+int dist_all_gather_inplace(Ctx* ctx, void* buf, size_t chunk_bytes, cudaStream_t st);
 
 // prove.cu
 int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,
