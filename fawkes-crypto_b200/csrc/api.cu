@@ -4,6 +4,7 @@
 
 #include <chrono>
 #include <cstring>
+#include <future>
 
 #include "internal.h"
 
@@ -54,6 +55,8 @@ __global__ void k_gather_bitrev(G1Affine* __restrict__ dst, const G1Affine* __re
   }
 }
 
+static void free_host_tables(void* p);
+static void* build_host_tables(const ProvingKey* pk);
 static void pk_release(ProvingKey* pk) {
   if (!pk) return;
   cudaFree(pk->h); cudaFree(pk->l); cudaFree(pk->a); cudaFree(pk->b1); cudaFree(pk->b2);
@@ -67,6 +70,7 @@ static void pk_release(ProvingKey* pk) {
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
   for (auto& e : pk->msm_done) if (e) cudaEventDestroy(e);
+  if (pk->host_tables) free_host_tables(pk->host_tables);
   delete pk;
 }
 
@@ -250,6 +254,7 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   for (auto& e : pk->msm_done) PK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   PK_CUDA(cudaMallocHost(&pk->results_host, 5 * MSM_VBITS * sizeof(G2XYZZ)));
   PK_CUDA(cudaStreamSynchronize(st));
+  pk->host_tables = build_host_tables(pk);
   *out = pk;
   return FB_OK;
 #undef PK_TRY
@@ -277,13 +282,45 @@ static H2 h2_from(const G2Affine& p) { return p.is_inf() ? H2::inf() : H2{HFq2::
 static G1Affine h1_affine(const H1& p) { Affine<HFq> a = to_affine(p); return {a.x.to(), a.y.to()}; }
 static G2Affine h2_affine(const H2& p) { Affine<HFq2> a = to_affine(p); return {a.x.to(), a.y.to()}; }
 
+// Fixed-base table of one key point for the host: T[w][d-1] = d * 16^w * P, so k * P is 64 additions
+// and no doublings.  Built once per key for delta_1, alpha_1, beta_1 (G1) and delta_2 (G2).
+template <class HP>
+struct HostTable {
+  std::vector<HP> t;  // 64 * 15
+  void build(const HP& p) {
+    t.resize(64 * 15);
+    HP base = p;
+    for (int w = 0; w < 64; w++) {
+      HP acc = base;
+      for (int d = 1; d <= 15; d++) {
+        t[w * 15 + d - 1] = acc;
+        acc = add(acc, base);
+      }
+      base = acc;  // 16 * base
+    }
+  }
+  HP mul(const uint32_t* k) const {  // k: 8 canonical 32-bit limbs
+    HP acc = HP::inf();
+    for (int w = 0; w < 64; w++) {
+      const uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+      if (d) acc = add(acc, t[w * 15 + d - 1]);
+    }
+    return acc;
+  }
+};
+struct KeyTables {
+  HostTable<H1> delta1, alpha1, beta1;
+  HostTable<H2> delta2;
+};
+
 struct FixedTerms {  // the parts of A, B, C that depend on r, s and the key only
   H1 a;   // alpha + r*delta
   H2 b;   // beta2 + s*delta2
   H1 c;   // rs*delta + s*alpha + r*beta1
   uint32_t rc[8], sc[8];
 };
-static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s[4], FixedTerms& f) {
+static int fixed_terms(const VkPoints* pk, const KeyTables* kt, const uint64_t r[4], const uint64_t s[4],
+                       FixedTerms& f) {
   if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) {
     set_error("UnexpectedIdentity: delta is the point at infinity");
     return FB_ERR_IDENTITY;
@@ -296,7 +333,16 @@ static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s
   memcpy(sm.v, s, 32);
   Fr rs = from_mont(mul(rm, sm));
   memcpy(rsc, rs.v, 32);
-  H1 d1 = h1_from(pk->delta_g1), al = h1_from(pk->alpha_g1), be1 = h1_from(pk->beta_g1);
+  H1 al = h1_from(pk->alpha_g1);
+  if (kt) {
+    f.a = add(kt->delta1.mul(f.rc), al);
+    f.b = add(kt->delta2.mul(f.sc), h2_from(pk->beta_g2));
+    f.c = kt->delta1.mul(rsc);
+    f.c = add(f.c, kt->alpha1.mul(f.sc));
+    f.c = add(f.c, kt->beta1.mul(f.rc));
+    return FB_OK;
+  }
+  H1 d1 = h1_from(pk->delta_g1), be1 = h1_from(pk->beta_g1);
   H2 d2 = h2_from(pk->delta_g2);
   f.a = add(scalar_mul(d1, f.rc), al);
   f.b = add(scalar_mul(d2, f.sc), h2_from(pk->beta_g2));
@@ -306,11 +352,11 @@ static int fixed_terms(const VkPoints* pk, const uint64_t r[4], const uint64_t s
   return FB_OK;
 }
 static void finish_proof(const FixedTerms& f, const H1& H, const H1& L, const H1& A, const H1& B1,
-                         const H2& B2, uint8_t proof_raw[256]) {
+                         const H2& B2, const H1* sA, const H1* rB1, uint8_t proof_raw[256]) {
   H1 g_a = add(f.a, A);
   H2 g_b = add(f.b, B2);
-  H1 g_c = add(f.c, scalar_mul(A, f.sc));
-  g_c = add(g_c, scalar_mul(B1, f.rc));
+  H1 g_c = add(f.c, sA ? *sA : scalar_mul(A, f.sc));
+  g_c = add(g_c, rB1 ? *rB1 : scalar_mul(B1, f.rc));
   g_c = add(g_c, H);
   g_c = add(g_c, L);
   G1Affine pa = h1_affine(g_a), pc = h1_affine(g_c);
@@ -322,10 +368,21 @@ static void finish_proof(const FixedTerms& f, const H1& H, const H1& L, const H1
 static int assemble(const VkPoints* pk, const H1& H, const H1& L, const H1& A, const H1& B1, const H2& B2,
                     const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]) {
   FixedTerms f;
-  int rc = fixed_terms(pk, r, s, f);
+  int rc = fixed_terms(pk, nullptr, r, s, f);
   if (rc) return rc;
-  finish_proof(f, H, L, A, B1, B2, proof_raw);
+  finish_proof(f, H, L, A, B1, B2, nullptr, nullptr, proof_raw);
   return FB_OK;
+}
+
+static void free_host_tables(void* p) { delete reinterpret_cast<KeyTables*>(p); }
+static void* build_host_tables(const ProvingKey* pk) {
+  if (pk->delta_g1.is_inf() || pk->delta_g2.is_inf()) return nullptr;  // prove reports UnexpectedIdentity
+  KeyTables* kt = new KeyTables();
+  kt->delta1.build(h1_from(pk->delta_g1));
+  kt->alpha1.build(h1_from(pk->alpha_g1));
+  kt->beta1.build(h1_from(pk->beta_g1));
+  kt->delta2.build(h2_from(pk->delta_g2));
+  return kt;
 }
 
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
@@ -444,25 +501,48 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));
   }
+  auto tl0 = std::chrono::steady_clock::now();
   int rc = prove_launch(pk, h_out);
   if (rc) { cudaDeviceSynchronize(); return rc; }
+  auto tl1 = std::chrono::steady_clock::now();
   // host work that needs only r, s and the key overlaps the device
   FixedTerms ft;
   VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
-  int rc_fixed = partial ? FB_OK : fixed_terms(&vk, r, s, ft);
+  int rc_fixed = partial ? FB_OK : fixed_terms(&vk, reinterpret_cast<const KeyTables*>(pk->host_tables), r, s, ft);
   // finish each MSM on the host as soon as its bit sums arrive (B2, B1, A, L finish while the
-  // device still runs the H pipeline and the H MSM)
-  FB_CUDA(cudaEventSynchronize(pk->msm_done[4]));
-  H2 B2 = msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.W * pk->plan_b.c);
-  FB_CUDA(cudaEventSynchronize(pk->msm_done[3]));
-  H1 B1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.W * pk->plan_b.c);
-  FB_CUDA(cudaEventSynchronize(pk->msm_done[2]));
-  H1 A = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.W * pk->plan_a.c);
+  // device still runs the H pipeline and the H MSM); the three heaviest tails get their own threads
+  const int dev = ctx->device;
+  const bool full = !partial && !rc_fixed;
+  auto fut_b2 = std::async(std::launch::async, [&, dev]() -> H2 {
+    cudaSetDevice(dev);
+    cudaEventSynchronize(pk->msm_done[4]);
+    return msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.W * pk->plan_b.c);
+  });
+  auto fut_b1 = std::async(std::launch::async, [&, dev]() -> std::pair<H1, H1> {
+    cudaSetDevice(dev);
+    cudaEventSynchronize(pk->msm_done[3]);
+    H1 b1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.W * pk->plan_b.c);
+    return {b1, full ? scalar_mul(b1, ft.rc) : H1::inf()};
+  });
+  auto fut_a = std::async(std::launch::async, [&, dev]() -> std::pair<H1, H1> {
+    cudaSetDevice(dev);
+    cudaEventSynchronize(pk->msm_done[2]);
+    H1 a = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.W * pk->plan_a.c);
+    return {a, full ? scalar_mul(a, ft.sc) : H1::inf()};
+  });
   FB_CUDA(cudaEventSynchronize(pk->msm_done[1]));
   H1 L = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 1), pk->plan_l.W * pk->plan_l.c);
   FB_CUDA(cudaEventSynchronize(pk->msm_done[0]));
   auto t1 = std::chrono::steady_clock::now();
   H1 H = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 0), pk->plan_h.W * pk->plan_h.c);
+  H2 B2 = fut_b2.get();
+  std::pair<H1, H1> pb1 = fut_b1.get(), pa = fut_a.get();
+  const H1 &B1 = pb1.first, &A = pa.first;
+  if (getenv("FB_TRACE")) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[fb trace] pre-launch %.3f  enqueue %.3f  fixed+waits %.3f  horner(H)+joins %.3f ms\n",
+            ms(t0, tl0), ms(tl0, tl1), ms(tl1, t1), ms(t1, std::chrono::steady_clock::now()));
+  }
   FB_CUDA(cudaStreamSynchronize(st));
   FB_CUDA(cudaGetLastError());
   if (rc_fixed) return rc_fixed;
@@ -477,7 +557,7 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     memcpy(partial + 512, &q, 128);
     rc = FB_OK;
   } else {
-    finish_proof(ft, H, L, A, B1, B2, proof_raw);
+    finish_proof(ft, H, L, A, B1, B2, &pa.second, &pb1.second, proof_raw);
     rc = FB_OK;
   }
   auto t2 = std::chrono::steady_clock::now();
@@ -637,6 +717,20 @@ int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, cons
   if (p && p->nshards != 1) { set_error("fb_prove on a sharded key: use fb_prove_partial"); return FB_ERR_ARG; }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), p, inputs, n_in, aux, n_aux, nullptr, r, s,
                     proof_raw, nullptr, h_out);
+}
+
+int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
+                   const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
+                   uint8_t* proofs_raw) {
+  if (!inputs || (!aux && n_aux) || !r || !s || !proofs_raw) { set_error("fb_prove_batch: null buffer"); return FB_ERR_ARG; }
+  // The reference proves one circuit per prove() call (prover.rs:63-90); a batch is the same key used
+  // `count` times.  Proofs are independent, so they are simply issued back to back on the resident key.
+  for (uint32_t i = 0; i < count; i++) {
+    int rc = fb_prove(ctx, pk, inputs[i], n_in, aux ? aux[i] : nullptr, n_aux, r + 4 * (size_t)i, s + 4 * (size_t)i,
+                      proofs_raw + 256 * (size_t)i, nullptr);
+    if (rc) return rc;
+  }
+  return FB_OK;
 }
 
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],

@@ -96,6 +96,7 @@ struct ProvingKey {
   int dist_g = 0;
   uint32_t n_gates_global = 0;
   Fr* xtmp[3] = {nullptr, nullptr, nullptr};
+  void* host_tables = nullptr;  // fixed-base tables of delta/alpha/beta for the host-side assembly
 };
 
 struct Circuit {

@@ -50,6 +50,7 @@ SIGNATURES = {
     "fb_pk_free": (None, [vp]),
     "fb_pk_get_info": (C.c_int, [vp, C.POINTER(PkInfo)]),
     "fb_prove": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp]),
+    "fb_prove_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
     "fb_prove_device": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "fb_prove_partial": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp]),
     "fb_prove_finish": (C.c_int, [vp, C.c_size_t, vp, C.c_int, vp, vp, vp]),

@@ -109,6 +109,11 @@ int fb_pk_get_info(const fb_pk* pk, fb_pk_info* info);
 int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
              uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
              uint64_t* h_out);
+/* `count` proofs on one resident key (BASELINE configs[1]: 256 eddsa proofs per run): inputs[i],
+ * aux[i] as for fb_prove; r, s: [count][4]; proofs_raw: [count][256]. */
+int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
+                   const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
+                   uint8_t* proofs_raw);
 /* Same, host buffers already on the device (dev_w = [inputs | aux] as Num<Fr>). */
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
                     const uint64_t s[4], uint8_t proof_raw[256]);

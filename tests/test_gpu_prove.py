@@ -190,3 +190,30 @@ def test_witness_with_zeros_and_ones(ctx):
     assert proof.to_raw() == codec.proof_raw(ref)
     assert fb.verify(params.get_vk(), proof, inputs)
     params.unload()
+
+
+def test_prove_batch_matches_single_proofs(ctx):
+    """fb_prove_batch (configs[1] shape: many proofs on one resident key) == proof-by-proof."""
+    import ctypes as C
+    import fawkes_crypto_b200 as fb
+    seed = synth.SEED_BASE + 5000
+    n_rows, count = 500, 5
+    gates, inp, aux = synth.synth_circuit(n_rows, seed)
+    td, r0, s0 = synth.synth_trapdoor(seed)
+    P = og.setup(gates, 2, len(aux), td)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
+    pk = params.load(ctx)
+    # the same satisfying witness with different blinding per proof
+    rs = [((r0 + 7 * i) % bn.R, (s0 + 11 * i) % bn.R) for i in range(count)]
+    wi, wa = fr_np(inp), fr_np(aux)
+    ins = (C.c_void_p * count)(*[wi.ctypes.data] * count)
+    axs = (C.c_void_p * count)(*[wa.ctypes.data] * count)
+    ra, sa = fr_np([x for x, _ in rs]), fr_np([y for _, y in rs])
+    out = np.zeros((count, 256), dtype=np.uint8)
+    fb.native.check(fb.native.lib.fb_prove_batch(ctx.handle, pk, count, ins, 2, axs, len(aux), ra.ctypes.data,
+                                                 sa.ctypes.data, out.ctypes.data))
+    for i, (r, s) in enumerate(rs):
+        ref = og.prove(P, gates, inp, aux, r, s)
+        assert out[i].tobytes() == codec.proof_raw(ref), i
+    params.unload()
