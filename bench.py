@@ -329,15 +329,19 @@ def run_ours(args):
     imad = C.c_double()
     fb.native.check(lib.fb_probe_imad(ctx.handle, C.byref(imad)))
     ach_mac = per_launch_adds * MAC32_PER_MIXED_ADD / (avg_ms * 1e-3) if avg_ms else 0.0
+    # DRAM traffic of one launch from the committed `ncu --set full` capture (profiles/r01_k_accumulate_g1.txt)
+    traffic = {20: 2.06e8}.get(args.log_rows) if world == 1 else None
     roofline = {"kernel": "k_accumulate<Fq> (G1 bucket accumulation)", "bound": "hbm", "achieved": ach_gbs,
-                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "traffic": None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": peaks["source"], "avg_launch_ms": avg_ms, "launches_timed": g1["launches"],
                 "algorithmic_bytes_per_launch": per_launch_adds * BYTES_PER_MIXED_ADD_G1,
-                "note": "algorithmic bytes = (64 B base + 4 B index) x n x W digits; the kernel is integer-pipe "
-                        "bound, see roofline_imad"}
+                "note": "algorithmic bytes = (64 B base + 4 B index) x n x W digits; traffic = dram read+write bytes of "
+                        "one launch (ncu, 2^20 capture only; below the algorithmic bytes because the base array "
+                        "is served from L2); the kernel is integer-pipe bound, see roofline_imad"}
     roofline_imad = {"kernel": roofline["kernel"], "bound": "imad", "achieved": ach_mac / 1e12,
                      "peak": imad.value / 1e12, "unit": "T MAC32/s", "frac": ach_mac / imad.value if imad.value else None,
-                     "peak_source": "measured live: dependent-free mad.wide.u32 streams (fb_probe_imad)",
+                     "peak_source": "measured live: dependent-free mad.wide.u32 streams (fb_probe_imad); real multi-limb "
+                                    "multiplier code saturates at ~0.5 of it (profiles/r01_rate_probe.txt)",
                      "algorithmic_mac32_per_launch": per_launch_adds * MAC32_PER_MIXED_ADD}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
