@@ -217,3 +217,18 @@ def test_prove_batch_matches_single_proofs(ctx):
         ref = og.prove(P, gates, inp, aux, r, s)
         assert out[i].tobytes() == codec.proof_raw(ref), i
     params.unload()
+
+
+def test_prove_2_20_bytes_equal_cpp_oracle(ctx):
+    """Full BASELINE size (configs[2], 2^20 rows): the GPU proof is byte-identical to the C++ CPU
+    restatement (itself byte-checked against the Python oracle in tests/test_oracle.py) and verifies."""
+    import fawkes_crypto_b200 as fb
+    import bench
+    from oracle import cpu
+    circ, params, tdi, _ = bench.make_case(fb, ctx, 20)
+    wi, wa = circ.witness()
+    inputs, proof = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
+    assert fb.verify(params.get_vk(), proof, inputs)
+    cproof, _ = bench.cpu_prove_once(fb, circ, params, tdi, cpu.hw_threads())
+    assert proof.to_raw() == cproof
+    params.unload()
