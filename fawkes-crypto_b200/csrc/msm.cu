@@ -15,7 +15,7 @@ MsmPlan MsmPlan::make(uint32_t n) {
   // window: accumulation costs n*W mixed adds, reduction ~2.6 * W * 2^(c-1) full adds
   int c = lg - 4;
   if (c < 4) c = 4;
-  if (c > 20) c = 20;
+  if (c > 17) c = 17;  // measured at 2^24: c = 17 (W = 15) beats 18..20, whose bucket arrays fall out of L2
   if (const char* e = getenv("FB_MSM_C")) {
     int v = atoi(e);
     if (v >= 2 && v <= 24) c = v;
