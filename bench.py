@@ -32,7 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED_BASE = 0xFA3CE50000
-MAC32_PER_MIXED_ADD = 10 * 136      # XYZZ madd: 8M + 2S, 136 32x32 MACs per Montgomery multiply
+# XYZZ mixed add = 6 multiplies (136 wide MACs: 64 product + 64 reduction + 8 quotient digits), 2 dedicated
+# squares (36 + 72) and one two-product sum sharing a reduction (128 + 72): the MACs this code has to issue.
+# (The textbook count for 8M + 2S with a generic multiplier is 10 * 136 = 1360.)
+MAC32_PER_MIXED_ADD = 6 * 136 + 2 * 108 + 200
 BYTES_PER_MIXED_ADD_G1 = 64 + 4     # one affine base + one sorted index
 BYTES_PER_MIXED_ADD_G2 = 128 + 4
 
@@ -340,8 +343,11 @@ def run_ours(args):
                         "is served from L2); the kernel is integer-pipe bound, see roofline_imad"}
     roofline_imad = {"kernel": roofline["kernel"], "bound": "imad", "achieved": ach_mac / 1e12,
                      "peak": imad.value / 1e12, "unit": "T MAC32/s", "frac": ach_mac / imad.value if imad.value else None,
-                     "peak_source": "measured live: dependent-free mad.wide.u32 streams (fb_probe_imad); real multi-limb "
-                                    "multiplier code saturates at ~0.5 of it (profiles/r01_rate_probe.txt)",
+                     "peak_source": "measured live: independent IMAD.WIDE.U32 accumulate streams, SASS-verified "
+                                    "(fb_probe_imad); the issue limit is one wide MAC per 4 cycles per SM "
+                                    "sub-partition = 148 SM x 32 lanes x SM clock (profiles/r01_pipe_probe.txt)",
+                     "peak_issue_limit": 148 * 32 * clocks.get("sm_mhz", 0) * 1e6 / 1e12 if clocks.get("sm_mhz") else None,
+                     "mac32_per_mixed_add": MAC32_PER_MIXED_ADD,
                      "algorithmic_mac32_per_launch": per_launch_adds * MAC32_PER_MIXED_ADD}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----

@@ -79,7 +79,7 @@ FB_HD XYZZ<F> add_mixed(const XYZZ<F>& a, const Affine<F>& q) {
   F PPP = mul(Pp, PP);
   F Q = mul(a.x, PP);
   F X3 = sub(sub(sqr(R), PPP), dbl(Q));
-  F Y3 = sub(mul(R, sub(Q, X3)), mul(a.y, PPP));
+  F Y3 = msub2(R, sub(Q, X3), a.y, PPP);
   return {X3, Y3, mul(a.zz, PP), mul(a.zzz, PPP)};
 }
 

@@ -12,6 +12,13 @@
 
 namespace fb {
 
+// (x + y u)(y + x u^... ) through the device Fq2 multiplier: returns c0 - c1 of (x + y u) * (y + x^2 u)
+__device__ inline Fq fq2_probe(const Fq& x, const Fq& y) {
+  Fq2 m = mul(Fq2{x, y}, Fq2{y, mul_c(x, x)});
+  return sub(m.c0, m.c1);
+}
+__device__ inline Fr fq2_probe(const Fr& x, const Fr&) { return x; }
+
 template <class C>
 __global__ void k_field_op(int op, const Fp<C>* a, const Fp<C>* b, Fp<C>* out, uint64_t n) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -22,6 +29,9 @@ __global__ void k_field_op(int op, const Fp<C>* a, const Fp<C>* b, Fp<C>* out, u
       case 1: r = add(x, y); break;
       case 2: r = sub(x, y); break;
       case 3: r = inv(x); break;
+      case 5: r = sqr(x); break;                         // dedicated square (36 + 72 wide MACs)
+      case 6: r = msub2(x, y, y, sqr(x)); break;         // x*y - y*x^2, one shared reduction
+      case 7: r = fq2_probe(x, y); break;                // Fq only: lazy-reduction Fq2 product
       default: r = mul_c(x, y); break;
     }
     out[i] = r;
@@ -61,21 +71,32 @@ __global__ void k_probe_imad_chain(uint64_t* out, uint32_t seed, int iters) {
   if (acc == 0x1234567812345678ull) out[0] = acc;
 }
 
+// Integer-pipe roofline probe: 8 independent IMAD.WIDE.U32 accumulate streams per thread.  The multiplier
+// operand is taken from another accumulator every round, so ptxas cannot hoist the products out of the
+// loop (an earlier version with loop-invariant operands was strength-reduced to IADD3 and reported the
+// ADD rate, 1.72e13/s, as the "MAC peak").  SASS of this loop: IMAD.WIDE.U32 only (checked with cuobjdump).
 __global__ void k_probe_imad(uint64_t* out, uint32_t seed, int iters) {
-  uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-  uint64_t acc[8];
+  uint32_t X[8][4], a[8];
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+  for (int j = 0; j < 8; j++) a[j] = seed * (2 * j + 3) + threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < 8; h++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) X[h][j] = seed * (j + 1) + h + threadIdx.x;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
-    }
+    for (int h = 0; h < 8; h++)  // the multiplier was written 8 MACs (half a round) earlier
+      asm volatile("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.u32 %1, %4, %6, %1;"
+                   "mad.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, %3;"
+                   : "+r"(X[h][0]), "+r"(X[h][1]), "+r"(X[h][2]), "+r"(X[h][3])
+                   : "r"(a[h]), "r"(a[(h + 3) & 7]), "r"(X[(h + 4) & 7][0]));
   }
-  uint64_t s = 0;
+  uint32_t s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) s ^= acc[j];
-  if (s == 0x1234567812345678ull) out[0] = s;  // keep the loop alive
+  for (int h = 0; h < 8; h++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) s ^= X[h][j];
+  if (s == 0x12345678u) out[0] = s;  // keep the loop alive
 }
 
 // carry-chained wide MACs exactly as the Montgomery rows issue them (IMAD.WIDE.U32.X)
@@ -346,7 +367,7 @@ int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) {
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms;
     cudaEventElapsedTime(&ms, e0, e1);
-    double rate = (double)blocks * threads * iters * 8 / (ms * 1e-3);
+    double rate = (double)blocks * threads * iters * 16 / (ms * 1e-3);
     if (rep > 0) best = std::max(best, rate);
   }
   *mac_per_s = best;

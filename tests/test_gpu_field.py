@@ -36,6 +36,12 @@ def test_field_ops_match_integers(ctx, field):
     assert to_list(run_op(ctx, field, 4, a, b)) == [x * y % mod for x, y in zip(av, bv)]      # portable mul
     assert to_list(run_op(ctx, field, 1, a, b)) == [(x + y) % mod for x, y in zip(av, bv)]
     assert to_list(run_op(ctx, field, 2, a, b)) == [(x - y) % mod for x, y in zip(av, bv)]
+    # dedicated square and the two-products-one-reduction form used by the mixed add
+    assert to_list(run_op(ctx, field, 5, a, b)) == [x * x % mod for x in av]
+    assert to_list(run_op(ctx, field, 6, a, b)) == [(x * y - y * x * x) % mod for x, y in zip(av, bv)]
+    if field == 1:  # Fq2 product with lazy reduction: (x + y u)(y + x^2 u), u^2 = -1, reported as c0 - c1
+        want = [((x * y - y * x * x) - (x * x * x + y * y)) % mod for x, y in zip(av, bv)]
+        assert to_list(run_op(ctx, field, 7, a, b)) == want
 
 
 @pytest.mark.parametrize("field", [0, 1])

@@ -1,0 +1,364 @@
+// Issue-rate probes for the sm_100a integer pipes and the candidate 256-bit multipliers.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr \
+//        -I fawkes-crypto_b200/csrc tools/pipe_probe.cu -o tools/pipe_probe
+// Prints cycles per warp-instruction per SMSP for each stream (from the SM clock) and multiplies/s.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "ff.cuh"
+#include "ff29.cuh"
+#include "ec.cuh"
+
+using namespace fb;
+
+#define REP8(X) X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7)
+
+// which: stream selector.  Every stream does `iters` rounds of a fixed unrolled body.  Multiplier operands come
+// from other accumulators so that ptxas cannot hoist the products out of the loop.
+#define CHAIN4(h, T)                                                                                         \
+  asm volatile("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1;"                               \
+               "madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3;"                              \
+               "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5;"                            \
+               "madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"                               \
+               : "+r"(X[h][0]), "+r"(X[h][1]), "+r"(X[h][2]), "+r"(X[h][3]), "+r"(X[h][4]), "+r"(X[h][5]),    \
+                 "+r"(X[h][6]), "+r"(X[h][7])                                                                 \
+               : "r"(a[4 * (h & 1)]), "r"(a[4 * (h & 1) + 1]), "r"(a[4 * (h & 1) + 2]), "r"(a[4 * (h & 1) + 3]), "r"(T))
+#define WIDE(j, B) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a[j]), "r"(B))
+#define ADDX(j) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(x[(j + 1) & 7]))
+template <int WHICH>
+__global__ void k_stream(uint32_t* out, uint32_t seed, int iters) {
+  uint32_t a[8], x[8], X[4][8];
+  uint64_t acc[8];
+  double d[8], e[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = seed * (2 * j + 3) + threadIdx.x;
+    acc[j] = j + threadIdx.x; x[j] = seed + j * threadIdx.x;
+    for (int h = 0; h < 4; h++) X[h][j] = seed * j + h + threadIdx.x;
+    d[j] = 1.0 + j + threadIdx.x * 1e-9; e[j] = 1.0 + 1e-7 * j;
+  }
+  for (int i = 0; i < iters; i++) {
+    if (WHICH == 0) {  // IMAD.WIDE plain, multiplier shared by the 8 MACs of a round
+      uint32_t t = (uint32_t)acc[7];
+#pragma unroll
+      for (int j = 0; j < 8; j++) WIDE(j, t);
+    } else if (WHICH == 1) {  // IMAD.WIDE plain, distinct multiplier per MAC
+#pragma unroll
+      for (int j = 0; j < 8; j++) WIDE(j, (uint32_t)acc[(j + 1) & 7]);
+    } else if (WHICH == 2) {  // four chains of 4 carry-linked wide MACs (carry out dropped)
+      CHAIN4(0, X[3][0]); CHAIN4(1, X[0][0]); CHAIN4(2, X[1][0]); CHAIN4(3, X[2][0]);
+    } else if (WHICH == 3) {  // 8 x (wide MAC with carry out + addc consuming it)
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        asm volatile("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
+                     : "+r"(X[j >> 2][2 * (j & 3)]), "+r"(X[j >> 2][2 * (j & 3) + 1]), "+r"(x[j]) : "r"(a[j]), "r"(x[(j + 1) & 7]));
+    } else if (WHICH == 4) {  // IMAD lo 32
+#pragma unroll
+      for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a[j]), "r"(x[(j + 1) & 7]));
+    } else if (WHICH == 5) {  // IMAD.HI
+#pragma unroll
+      for (int j = 0; j < 8; j++) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(x[j]) : "r"(a[j]), "r"(x[(j + 1) & 7]));
+    } else if (WHICH == 6) {  // IADD3 stream
+#pragma unroll
+      for (int j = 0; j < 8; j++) ADDX(j);
+    } else if (WHICH == 7) {  // carry chain of 8 adds
+      asm volatile("add.cc.u32 %0, %0, %1; addc.cc.u32 %1, %1, %2; addc.cc.u32 %2, %2, %3; addc.cc.u32 %3, %3, %4;"
+                   "addc.cc.u32 %4, %4, %5; addc.cc.u32 %5, %5, %6; addc.cc.u32 %6, %6, %7; addc.u32 %7, %7, %0;"
+                   : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]));
+    } else if (WHICH == 8 || WHICH == 9 || WHICH == 10) {  // 8 plain wide MACs + 4 / 8 / 16 independent alu ops
+      uint32_t t = (uint32_t)acc[7];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        WIDE(j, t);
+        if (WHICH == 8 && (j & 1)) ADDX(j);
+        if (WHICH == 9) ADDX(j);
+        if (WHICH == 10) { ADDX(j); asm volatile("xor.b32 %0, %0, %1;" : "+r"(X[0][j]) : "r"(x[j])); }
+      }
+    } else if (WHICH == 11) {  // four carry chains of 4 + 16 alu ops
+      CHAIN4(0, X[3][0]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) ADDX(j);
+      CHAIN4(1, X[0][0]);
+#pragma unroll
+      for (int j = 4; j < 8; j++) ADDX(j);
+      CHAIN4(2, X[1][0]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) ADDX(j);
+      CHAIN4(3, X[2][0]);
+#pragma unroll
+      for (int j = 4; j < 8; j++) ADDX(j);
+    } else if (WHICH == 12) {  // DFMA stream
+#pragma unroll
+      for (int j = 0; j < 8; j++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+    } else if (WHICH == 13) {  // 8 DFMA + 8 plain wide MACs
+      uint32_t t = (uint32_t)acc[7];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+        WIDE(j, t);
+      }
+    } else if (WHICH == 14) {  // 16 DFMA + four carry chains of 4
+      CHAIN4(0, X[3][0]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+      CHAIN4(1, X[0][0]);
+#pragma unroll
+      for (int j = 4; j < 8; j++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+      CHAIN4(2, X[1][0]);
+#pragma unroll
+      for (int j = 0; j < 4; j++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+      CHAIN4(3, X[2][0]);
+#pragma unroll
+      for (int j = 4; j < 8; j++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[j]) : "d"(e[j]), "d"(e[0]));
+    } else if (WHICH == 15) {  // wide MAC, 64-bit addend read from a different pair (3-address form)
+      uint32_t t = (uint32_t)acc[7];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        asm volatile("mad.wide.u32 %0, %2, %3, %1;" : "=l"(acc[j]) : "l"(acc[j + 1]), "r"(a[j]), "r"(t));
+        asm volatile("mad.wide.u32 %0, %2, %3, %1;" : "=l"(acc[j + 1]) : "l"(acc[j]), "r"(a[j + 1]), "r"(t));
+      }
+    } else if (WHICH == 16) {  // 8 wide MACs each with carry OUT only (mad.lo.cc + madc.hi.cc, flag consumed every 4th)
+#pragma unroll
+      for (int h = 0; h < 4; h++)
+        asm volatile("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.u32 %1, %4, %6, %1;"
+                     "mad.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, %3;"
+                     : "+r"(X[h][0]), "+r"(X[h][1]), "+r"(X[h][2]), "+r"(X[h][3]) : "r"(a[h]), "r"(a[h + 4]), "r"(X[(h + 1) & 3][0]));
+    }
+  }
+  uint32_t s = 0;
+  double ds = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) { s ^= (uint32_t)acc[j] ^ (uint32_t)(acc[j] >> 32) ^ x[j] ^ X[0][j] ^ X[1][j] ^ X[2][j] ^ X[3][j]; ds += d[j]; }
+  if (s == 0x12345678u && ds == 1.2345) out[0] = s;
+}
+
+template <int V>
+__global__ void k_mul(Fr* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fr x = Fr::one(), y = Fr::r2();
+  x.v[0] += threadIdx.x;
+  y.v[1] ^= blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+    if (V == 0) { x = mul_ptx(x, y); y = mul_ptx(y, x); }
+    else if (V == 1) { x = mul_v2(x, y); y = mul_v2(y, x); }
+  }
+  if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
+#endif
+}
+// two independent multiply chains per thread (more ILP)
+template <int V>
+__global__ void k_mul2(Fr* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fr x = Fr::one(), y = Fr::r2(), z = Fr::r2(), w = Fr::one();
+  x.v[0] += threadIdx.x; y.v[1] ^= blockIdx.x + 3 * threadIdx.x; z.v[2] ^= threadIdx.x; w.v[1] += blockIdx.x;
+  for (int i = 0; i < iters; i++) {
+    if (V == 0) { x = mul_ptx(x, y); z = mul_ptx(z, w); y = mul_ptx(y, x); w = mul_ptx(w, z); }
+    else { x = mul_v2(x, y); z = mul_v2(z, w); y = mul_v2(y, x); w = mul_v2(w, z); }
+  }
+  if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u && z.v[1] == 5 && w.v[2] == 7) out[0] = x;
+#endif
+}
+__device__ Fq2 fq2_mul_old(const Fq2& a, const Fq2& b) {
+#if defined(__CUDA_ARCH__)
+  Fq t0 = mul_ptx(a.c0, b.c0);
+  Fq t1 = mul_ptx(a.c1, b.c1);
+  Fq t2 = mul_ptx(add(a.c0, a.c1), add(b.c0, b.c1));
+  return {sub(t0, t1), sub(sub(t2, t0), t1)};
+#else
+  return a;
+#endif
+}
+template <class F>
+__device__ F rnd(uint32_t& st) {  // xorshift-filled element, reduced by clearing the top bits
+  F x;
+  for (int k = 0; k < 8; k++) { st ^= st << 13; st ^= st >> 17; st ^= st << 5; x.v[k] = st; }
+  x.v[7] &= 0x1fffffffu;  // < 2^253 < p
+  return x;
+}
+template <class F>
+__device__ F edge(int which) {
+  F x = F::zero();
+  if (which == 1) x = F::one();
+  if (which == 2) { for (int k = 0; k < 8; k++) x.v[k] = F::Cfg::mod(k); x.v[0] -= 1; }  // p - 1
+  if (which == 3) { x.v[0] = 1; }
+  if (which == 4) { for (int k = 0; k < 7; k++) x.v[k] = 0xffffffffu; x.v[7] = 0x1fffffffu; }
+  return x;
+}
+// bad[0] mul_v2, [1] sqr, [2] msub2, [3] fq2 mul, [4] add_mixed Fq, [5] add_mixed Fq2
+template <class F>
+__global__ void k_check(uint32_t* bad, int n) {
+#if defined(__CUDA_ARCH__)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t st = 0x9e3779b9u * (i + 1) + 12345u;
+  for (int r = 0; r < 24; r++) {
+    F a = r < 5 ? edge<F>(r) : rnd<F>(st), b = (r % 7 == 3) ? edge<F>((r + i) % 5) : rnd<F>(st);
+    F c = rnd<F>(st), d = (r % 5 == 1) ? edge<F>((r + i) % 5) : rnd<F>(st);
+    if (r == 6) c = F::zero();
+    if (r == 7) { c = a; d = b; }
+    F ref = mul_c(a, b);
+    if (mul_v2(a, b) != ref || mul_ptx(a, b) != ref) atomicAdd(&bad[0], 1u);
+    if (mul_v3(a, b) != ref) atomicAdd(&bad[4], 1u);
+    if (dot2_v3(a, b, pneg_raw(c), d) != sub_c(mul_c(a, b), mul_c(c, d))) atomicAdd(&bad[5], 1u);
+    if (sqr_ptx(a) != mul_c(a, a)) atomicAdd(&bad[1], 1u);
+    if (msub2(a, b, c, d) != sub_c(mul_c(a, b), mul_c(c, d))) atomicAdd(&bad[2], 1u);
+    Fq2 x{Fq{}, Fq{}}, y{Fq{}, Fq{}};
+    for (int k = 0; k < 8; k++) { x.c0.v[k] = a.v[k]; x.c1.v[k] = b.v[k]; y.c0.v[k] = c.v[k]; y.c1.v[k] = d.v[k]; }
+    if (sizeof(typename F::Cfg) && F::Cfg::INV == FqCfg::INV) {
+      Fq2 m1 = mul(x, y), m2 = fq2_mul_old(x, y);
+      if (m1 != m2) atomicAdd(&bad[3], 1u);
+      Fq2 rc0{mul_c(x.c0, y.c0), Fq::zero()};
+      if (m1.c0 != sub_c(mul_c(x.c0, y.c0), mul_c(x.c1, y.c1))) atomicAdd(&bad[3], 1u);
+      if (m1.c1 != add_c(mul_c(x.c0, y.c1), mul_c(x.c1, y.c0))) atomicAdd(&bad[3], 1u);
+    }
+  }
+#endif
+}
+
+// throughput kernels: V = 0 mul_v2, 1 sqr_ptx, 2 msub2, 3 mul_ptx
+template <int V>
+__global__ void k_rate(Fq* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fq x = Fq::one(), y = Fq::r2(), z = Fq::r2();
+  x.v[0] += threadIdx.x; y.v[1] ^= blockIdx.x + 3 * threadIdx.x; z.v[2] ^= threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+    if (V == 0) { x = mul_v2(x, y); y = mul_v2(y, x); }
+    else if (V == 1) { x = sqr_ptx(x); y = sqr_ptx(y); }
+    else if (V == 2) { x = msub2(x, y, z, x); y = msub2(y, x, z, y); }
+    else if (V == 4) { x = mul_v3(x, y); y = mul_v3(y, x); }
+    else if (V == 5) { x = dot2_v3(x, y, z, x); y = dot2_v3(y, x, z, y); }
+    else { x = mul_ptx(x, y); y = mul_ptx(y, x); }
+  }
+  if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
+#endif
+}
+template <int V>
+__global__ void k_rate2(Fq2* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fq2 x = Fq2::one(), y = Fq2::one();
+  x.c0.v[0] += threadIdx.x; x.c1.v[1] = blockIdx.x + 5; y.c1.v[2] = threadIdx.x + 1; y.c0.v[3] ^= 77;
+  for (int i = 0; i < iters; i++) {
+    if (V == 0) { x = mul(x, y); y = mul(y, x); }
+    else { x = fq2_mul_old(x, y); y = fq2_mul_old(y, x); }
+  }
+  if (x.c0.v[0] == 0x12345678u && y.c1.v[3] == 0x9abcdef0u) out[0] = x;
+#endif
+}
+// mixed-add throughput: acc += P_k over a small table of affine points (all in registers / L1)
+template <class F>
+__global__ void k_rate_madd(const Affine<F>* pts, XYZZ<F>* out, int iters) {
+  XYZZ<F> acc = XYZZ<F>::from_affine(pts[threadIdx.x & 15]);
+  for (int i = 0; i < iters; i++) acc = add_mixed(acc, pts[16 + ((i + threadIdx.x) & 15)]);
+  if (acc.x.is_zero()) out[0] = acc;
+}
+template <class F>
+__global__ void k_make_pts(Affine<F>* pts, F b) {
+  // 32 distinct points: k * G for a generator found by x = 1, 2 (G1) / fixed G2 generator is not needed:
+  // any curve point works for timing, so use P, 2P, 3P, ... of the first valid point passed in pts[0]
+  XYZZ<F> acc = XYZZ<F>::from_affine(pts[0]);
+  Affine<F> g = pts[0];
+  for (int k = 1; k < 32; k++) { acc = add_mixed(acc, g); pts[k] = to_affine(acc); }
+}
+
+static double run(void (*launch)(int, int, int, void*), int threads, int bps, int iters, void* d) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  launch(threads, bps * 148, iters / 8, d);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0);
+    launch(threads, bps * 148, iters, d);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  return best * 1e-3;
+}
+
+#define STREAM_LAUNCH(W) [](int t, int b, int it, void* d) { k_stream<W><<<b, t>>>((uint32_t*)d, 777u, it); }
+
+int main(int argc, char** argv) {
+  void* d; cudaMalloc(&d, 1 << 20);
+  cudaMemset(d, 0, 1 << 20);
+  int clk_khz = 0; cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  printf("sm clock (attr) %d kHz\n", clk_khz);
+  struct S { const char* name; void (*fn)(int, int, int, void*); int inst; };
+  S streams[] = {
+    {"0 wide plain, shared b        (8 fma)", STREAM_LAUNCH(0), 8},
+    {"1 wide plain, distinct ops    (8 fma)", STREAM_LAUNCH(1), 8},
+    {"2 4x chain4 carry, no out    (16 fma)", STREAM_LAUNCH(2), 16},
+    {"3 8x(wide cc-out + addc)  (8 fma+8 alu)", STREAM_LAUNCH(3), 8},
+    {"4 imad lo                     (8 fma)", STREAM_LAUNCH(4), 8},
+    {"5 imad hi                     (8 fma)", STREAM_LAUNCH(5), 8},
+    {"6 iadd                        (8 alu)", STREAM_LAUNCH(6), 8},
+    {"7 add carry chain of 8        (8 alu)", STREAM_LAUNCH(7), 8},
+    {"8 8 wide + 4 add", STREAM_LAUNCH(8), 8},
+    {"9 8 wide + 8 add", STREAM_LAUNCH(9), 8},
+    {"10 8 wide + 16 alu", STREAM_LAUNCH(10), 8},
+    {"11 4x chain4 + 16 add  (16 fma+16 alu)", STREAM_LAUNCH(11), 16},
+    {"12 8 dfma", STREAM_LAUNCH(12), 8},
+    {"13 8 dfma + 8 wide", STREAM_LAUNCH(13), 8},
+    {"14 16 dfma + 4x chain4", STREAM_LAUNCH(14), 16},
+    {"15 wide plain 3-address", STREAM_LAUNCH(15), 8},
+    {"16 8 wide (lo.cc+hi pairs, no carry use)", STREAM_LAUNCH(16), 8},
+  };
+  const double f = 1.92e9;  // nominal; the ratio between rows is what matters
+  if (argc > 1) for (auto& s : streams) {
+    for (int cfg = 0; cfg < 2; cfg++) {
+      int threads = cfg == 0 ? 256 : 512, bps = 4, iters = 1 << 14;
+      double t = run(s.fn, threads, bps, iters, d);
+      double warps_per_smsp = threads * bps / 128.0;
+      // cycles per unrolled body per warp slot on one SMSP
+      double cyc = t * f / iters / warps_per_smsp;
+      printf("%-42s warps/SMSP=%4.0f  %.2f cycles per body (8 primary instr)  [%.3e bodies/s]\n", s.name, warps_per_smsp,
+             cyc, (double)iters * threads * bps * 148 / t);
+    }
+  }
+  uint32_t* bad = (uint32_t*)d;
+  cudaMemset(bad, 0, 64);
+  k_check<Fq><<<64, 128>>>(bad, 64 * 128);
+  k_check<Fr><<<64, 128>>>(bad, 64 * 128);
+  uint32_t hb[8]; cudaMemcpy(hb, bad, 32, cudaMemcpyDeviceToHost);
+  printf("mismatches: mul %u sqr %u msub2 %u fq2mul %u mul_v3 %u dot2_v3 %u (%s)\n", hb[0], hb[1], hb[2], hb[3], hb[4], hb[5], cudaGetErrorString(cudaGetLastError()));
+  struct M { const char* name; void (*fn)(int, int, int, void*); int per; };
+  M muls[] = {
+    {"mul_ptx", [](int t, int b, int it, void* d) { k_rate<3><<<b, t>>>((Fq*)d, it); }, 2},
+    {"mul_v2", [](int t, int b, int it, void* d) { k_rate<0><<<b, t>>>((Fq*)d, it); }, 2},
+    {"mul_v3 (karatsuba)", [](int t, int b, int it, void* d) { k_rate<4><<<b, t>>>((Fq*)d, it); }, 2},
+    {"dot2_v3 (karatsuba)", [](int t, int b, int it, void* d) { k_rate<5><<<b, t>>>((Fq*)d, it); }, 2},
+    {"sqr_ptx", [](int t, int b, int it, void* d) { k_rate<1><<<b, t>>>((Fq*)d, it); }, 2},
+    {"msub2 (2 products)", [](int t, int b, int it, void* d) { k_rate<2><<<b, t>>>((Fq*)d, it); }, 2},
+    {"fq2 mul lazy", [](int t, int b, int it, void* d) { k_rate2<0><<<b, t>>>((Fq2*)d, it); }, 2},
+    {"fq2 mul old", [](int t, int b, int it, void* d) { k_rate2<1><<<b, t>>>((Fq2*)d, it); }, 2},
+  };
+  for (auto& m : muls) {
+    for (int cfg = 0; cfg < 2; cfg++) {
+      int threads = cfg == 0 ? 128 : 256, bps = 4, iters = 1 << 11;
+      double t = run(m.fn, threads, bps, iters, d);
+      double warps_per_smsp = threads * bps / 128.0;
+      double ops_s = (double)iters * m.per * threads * bps * 148 / t;
+      printf("%-22s warps/SMSP=%4.0f  %.3e /s   %.0f cycles per warp-op per SMSP\n", m.name, warps_per_smsp, ops_s,
+             148.0 * 4 * 32 * f / ops_s);
+    }
+  }
+  {  // mixed-add rate, G1
+    G1Affine* pts = (G1Affine*)((char*)d + 4096);
+    G1Affine g; g.x = Fq::one(); g.y = Fq::one(); g.y = add_c(g.y, g.y);  // (1, 2) in Montgomery form
+    cudaMemcpy(pts, &g, sizeof(g), cudaMemcpyHostToDevice);
+    k_make_pts<Fq><<<1, 1>>>(pts, Fq::zero());
+    cudaDeviceSynchronize();
+    static G1Affine* spts; spts = pts;
+    auto fn = [](int t, int b, int it, void* d) { k_rate_madd<Fq><<<b, t>>>(spts, (G1XYZZ*)d, it); };
+    for (int cfg = 0; cfg < 2; cfg++) {
+      int threads = 128, bps = cfg == 0 ? 3 : 4, iters = 1 << 9;
+      double t = run(fn, threads, bps, iters, d);
+      double adds_s = (double)iters * threads * bps * 148 / t;
+      printf("G1 add_mixed           warps/SMSP=%4.0f  %.3e adds/s   %.0f cycles per warp-add per SMSP (%s)\n",
+             threads * bps / 128.0, adds_s, 148.0 * 4 * 32 * f / adds_s, cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  return 0;
+}
