@@ -164,6 +164,32 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     cnt = n * (shard + 1) / nshards - lo;
   };
   uint64_t lo, cnt;
+  // MSM plans first: in window-table mode every base array is allocated W times larger
+  {
+    uint64_t cnt_h, cnt_l, cnt_a, cnt_b;
+    slice(m - 1, lo, cnt_h);
+    if (dist_g) cnt_h = std::min<uint64_t>(ml, (m - 1) - (uint64_t)shard * ml);
+    slice(v.n_l, lo, cnt_l);
+    slice(v.n_a, lo, cnt_a);
+    slice(v.n_b1, lo, cnt_b);
+    bool tables = g_msm_tables == 1;
+    if (g_msm_tables < 0) {
+      const MsmPlan th = MsmPlan::make((uint32_t)cnt_h, true), tl = MsmPlan::make((uint32_t)cnt_l, true),
+                    ta = MsmPlan::make((uint32_t)cnt_a, true), tb = MsmPlan::make((uint32_t)cnt_b, true);
+      const uint64_t need = (th.table_points() + tl.table_points() + ta.table_points()) * 64 + tb.table_points() * 192;
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      // everything else a key holds (CSR, twiddles, workspaces, MSM scratch) is ~25 x 32 B per row
+      tables = need + (uint64_t)m * 32 * 25 + (8ull << 30) < free_b;
+    }
+    pk->plan_h = MsmPlan::make((uint32_t)cnt_h, tables);
+    pk->plan_l = MsmPlan::make((uint32_t)cnt_l, tables);
+    pk->plan_a = MsmPlan::make((uint32_t)cnt_a, tables);
+    pk->plan_b = MsmPlan::make((uint32_t)cnt_b, tables);
+    pk->table_bytes = tables ? (pk->plan_h.table_points() - cnt_h + pk->plan_l.table_points() - cnt_l +
+                                pk->plan_a.table_points() - cnt_a) * 64 + (pk->plan_b.table_points() - cnt_b) * 192
+                             : 0;
+  }
   // h: decode all to a temporary, gather this shard's bit-reversed positions
   {
     const uint64_t nh = m - 1;
@@ -178,27 +204,27 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
       cnt = std::min<uint64_t>(ml, nh - lo);
     }
     pk->len_h = (uint32_t)cnt;
-    PK_CUDA(cudaMalloc(&pk->h, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+    PK_CUDA(cudaMalloc(&pk->h, std::max<uint64_t>(pk->plan_h.table_points(), 1) * sizeof(G1Affine)));
     if (cnt) k_gather_bitrev<<<(unsigned)std::min<uint64_t>((cnt + 255) / 256, 148 * 16), 256, 0, st>>>(
         pk->h, tmp, k, (uint32_t)lo, (uint32_t)cnt);
     PK_CUDA(cudaStreamSynchronize(st));
     cudaFree(tmp);
   }
   slice(v.n_l, lo, cnt);
-  PK_CUDA(cudaMalloc(&pk->l, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_CUDA(cudaMalloc(&pk->l, std::max<uint64_t>(pk->plan_l.table_points(), 1) * sizeof(G1Affine)));
   PK_TRY(decode_g1_be(v.l + lo * 64, cnt, pk->l, checked, st));
   slice(v.n_a, lo, cnt);
   pk->len_a = (uint32_t)cnt;
-  PK_CUDA(cudaMalloc(&pk->a, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_CUDA(cudaMalloc(&pk->a, std::max<uint64_t>(pk->plan_a.table_points(), 1) * sizeof(G1Affine)));
   PK_TRY(decode_g1_be(v.a + lo * 64, cnt, pk->a, checked, st));
   PK_CUDA(cudaMalloc(&pk->a_map, std::max<uint64_t>(cnt, 1) * 4));
   PK_CUDA(cudaMemcpyAsync(pk->a_map, a_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice, st));
   PK_CUDA(cudaStreamSynchronize(st));
   slice(v.n_b1, lo, cnt);
   pk->len_b = (uint32_t)cnt;
-  PK_CUDA(cudaMalloc(&pk->b1, std::max<uint64_t>(cnt, 1) * sizeof(G1Affine)));
+  PK_CUDA(cudaMalloc(&pk->b1, std::max<uint64_t>(pk->plan_b.table_points(), 1) * sizeof(G1Affine)));
   PK_TRY(decode_g1_be(v.b1 + lo * 64, cnt, pk->b1, checked, st));
-  PK_CUDA(cudaMalloc(&pk->b2, std::max<uint64_t>(cnt, 1) * sizeof(G2Affine)));
+  PK_CUDA(cudaMalloc(&pk->b2, std::max<uint64_t>(pk->plan_b.table_points(), 1) * sizeof(G2Affine)));
   PK_TRY(decode_g2_be(v.b2 + lo * 128, cnt, pk->b2, checked, st));
   PK_CUDA(cudaMalloc(&pk->b_map, std::max<uint64_t>(cnt, 1) * 4));
   PK_CUDA(cudaMemcpyAsync(pk->b_map, b_map.data() + lo, cnt * 4, cudaMemcpyHostToDevice, st));
@@ -236,15 +262,21 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   PK_CUDA(cudaMalloc(&pk->scratch, ml * sizeof(Fr)));
   if (dist_g)
     for (int i = 0; i < 3; i++) PK_CUDA(cudaMalloc(&pk->xtmp[i], ml * sizeof(Fr)));
-  uint64_t l_lo, l_cnt;
-  slice(v.n_l, l_lo, l_cnt);
-  pk->plan_h = MsmPlan::make(pk->len_h);
-  pk->plan_l = MsmPlan::make((uint32_t)l_cnt);
-  pk->plan_a = MsmPlan::make(pk->len_a);
-  pk->plan_b = MsmPlan::make(pk->len_b);
-  const uint64_t msm_sizes[4] = {pk->len_h, l_cnt, pk->len_a, pk->len_b};
+  if (pk->plan_h.n != pk->len_h || pk->plan_a.n != pk->len_a || pk->plan_b.n != pk->len_b) {
+    set_error("internal: MSM plan sizes disagree with the loaded shard");
+    pk_release(pk);
+    return FB_ERR_ARG;
+  }
+  // window tables: 2^(c w) P for every window, next to the bases (once per key)
+  PK_TRY(msm_build_table_g1(pk->h, pk->plan_h, st) ? FB_ERR_CUDA : 0);
+  PK_TRY(msm_build_table_g1(pk->l, pk->plan_l, st) ? FB_ERR_CUDA : 0);
+  PK_TRY(msm_build_table_g1(pk->a, pk->plan_a, st) ? FB_ERR_CUDA : 0);
+  PK_TRY(msm_build_table_g1(pk->b1, pk->plan_b, st) ? FB_ERR_CUDA : 0);
+  PK_TRY(msm_build_table_g2(pk->b2, pk->plan_b, st) ? FB_ERR_CUDA : 0);
+  PK_CUDA(cudaStreamSynchronize(st));
+  const MsmPlan msm_plans[4] = {pk->plan_h, pk->plan_l, pk->plan_a, pk->plan_b};
   int arc = 0;
-  for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_sizes[i], 1, i == 3);
+  for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_plans[i], 1, i == 3);
   if (arc != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
@@ -385,6 +417,7 @@ static void* build_host_tables(const ProvingKey* pk) {
   return kt;
 }
 
+int g_msm_tables = -1;
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
 
 // Result slots: five arrays of MSM_VBITS bit sums (G2-sized slots), order H L A B1 B2.
@@ -516,25 +549,25 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
   auto fut_b2 = std::async(std::launch::async, [&, dev]() -> H2 {
     cudaSetDevice(dev);
     cudaEventSynchronize(pk->msm_done[4]);
-    return msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.W * pk->plan_b.c);
+    return msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.vbits());
   });
   auto fut_b1 = std::async(std::launch::async, [&, dev]() -> std::pair<H1, H1> {
     cudaSetDevice(dev);
     cudaEventSynchronize(pk->msm_done[3]);
-    H1 b1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.W * pk->plan_b.c);
+    H1 b1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.vbits());
     return {b1, full ? scalar_mul(b1, ft.rc) : H1::inf()};
   });
   auto fut_a = std::async(std::launch::async, [&, dev]() -> std::pair<H1, H1> {
     cudaSetDevice(dev);
     cudaEventSynchronize(pk->msm_done[2]);
-    H1 a = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.W * pk->plan_a.c);
+    H1 a = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.vbits());
     return {a, full ? scalar_mul(a, ft.sc) : H1::inf()};
   });
   FB_CUDA(cudaEventSynchronize(pk->msm_done[1]));
-  H1 L = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 1), pk->plan_l.W * pk->plan_l.c);
+  H1 L = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 1), pk->plan_l.vbits());
   FB_CUDA(cudaEventSynchronize(pk->msm_done[0]));
   auto t1 = std::chrono::steady_clock::now();
-  H1 H = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 0), pk->plan_h.W * pk->plan_h.c);
+  H1 H = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 0), pk->plan_h.vbits());
   H2 B2 = fut_b2.get();
   std::pair<H1, H1> pb1 = fut_b1.get(), pa = fut_a.get();
   const H1 &B1 = pb1.first, &A = pa.first;
@@ -701,7 +734,7 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
   uint64_t b = (uint64_t)pk->len_h * 64 + (uint64_t)pk->plan_l.n * 64 + (uint64_t)pk->len_a * 68 +
                (uint64_t)pk->len_b * (64 + 128 + 4) + info->nnz * 8 + 5 * pk->m * 32 +
                3 * (pk->m - 1) * 32 + (uint64_t)(pk->n_in + pk->n_aux) * 32;
-  info->hbm_bytes = b;
+  info->hbm_bytes = b + pk->table_bytes;
   info->g1_digit_slots = (uint64_t)pk->plan_h.n * pk->plan_h.W + (uint64_t)pk->plan_l.n * pk->plan_l.W +
                          (uint64_t)pk->plan_a.n * pk->plan_a.W + (uint64_t)pk->plan_b.n * pk->plan_b.W;
   info->g2_digit_slots = (uint64_t)pk->plan_b.n * pk->plan_b.W;
@@ -794,6 +827,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
 
 uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
+void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {

@@ -17,6 +17,8 @@
 namespace fb {
 
 void set_error(const char* fmt, ...);
+// MSM window tables (msm.cuh): -1 auto (on when the tables fit in free HBM with headroom), 0 off, 1 on
+extern int g_msm_tables;
 
 // ---- instrumentation (bench.py: gpu_launches and the live roofline timing) -------------
 extern unsigned long long g_launches;           // kernels launched by this library
@@ -97,6 +99,7 @@ struct ProvingKey {
   uint32_t n_gates_global = 0;
   Fr* xtmp[3] = {nullptr, nullptr, nullptr};
   void* host_tables = nullptr;  // fixed-base tables of delta/alpha/beta for the host-side assembly
+  uint64_t table_bytes = 0;     // HBM held by the MSM window tables beyond the plain base arrays
 };
 
 struct Circuit {

@@ -2,23 +2,43 @@
 #include "msm.cuh"
 #include "internal.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace fb {
 
 // ------------------------------------------------------------------ plan ---
-MsmPlan MsmPlan::make(uint32_t n) {
+MsmPlan MsmPlan::make(uint32_t n, bool table) {
   MsmPlan p;
   p.n = n;
+  p.table = table;
   int lg = 0;
   while ((2u << lg) <= n && lg < 31) lg++;
-  // window: accumulation costs n*W mixed adds, reduction ~2.6 * W * 2^(c-1) full adds
-  int c = lg - 4;
+  int c;
+  if (table) {
+    // One bucket set for all windows: n*W mixed adds to accumulate, and sort + reduction work per bucket
+    // worth ~20 mixed adds (measured: 2^24 rows c = 20 beats 22 by 9 ms, 2^20 rows c = 17 beats 19 by
+    // 1.5 ms; profiles/r01_window_sweep.txt).  Windows whose top digit has only a few bits are skipped:
+    // all n top digits would land in a handful of buckets (c = 21 / 23 at 2^24 cost +30 / +70 ms).
+    double best = 1e300;
+    c = 0;
+    for (int cand = std::max(4, lg - 6); cand <= std::min(22, std::max(4, lg)); cand++) {
+      const int Wc = (255 + cand - 1) / cand;
+      const int top_bits = 254 - (Wc - 1) * cand;
+      if (2 * top_bits < cand) continue;
+      const double cost = (double)n * Wc + 20.0 * (double)(1u << (cand - 1));
+      if (cost < best) { best = cost; c = cand; }
+    }
+    if (c == 0) c = std::max(4, std::min(22, lg - 3));
+  } else {
+    // accumulation costs n*W mixed adds, reduction ~2.6 * W * 2^(c-1) full adds
+    c = lg - 4;
+    if (c > 17) c = 17;  // measured at 2^24: c = 17 (W = 15) beats 18..20, whose bucket arrays fall out of L2
+  }
   if (c < 4) c = 4;
-  if (c > 17) c = 17;  // measured at 2^24: c = 17 (W = 15) beats 18..20, whose bucket arrays fall out of L2
-  if (const char* e = getenv("FB_MSM_C")) {
+  if (const char* e = getenv(table ? "FB_MSM_TABLE_C" : "FB_MSM_C")) {
     int v = atoi(e);
-    if (v >= 2 && v <= 24) c = v;
+    if (v >= 4 && v <= 24) c = v;
   }
   p.c = c;
   p.W = (255 + c - 1) / c;
@@ -33,15 +53,23 @@ MsmPlan MsmPlan::make(uint32_t n) {
   return p;
 }
 
-int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
+// segments one k_segment_bits CTA folds (per (window, bit) job the segment range is cut into parts)
+constexpr int MSM_BITS_PART_LOG = 11;
+static inline int bits_parts(const MsmPlan& p) {
+  const int sbits = p.c - 1 - p.seg_log;
+  return sbits > MSM_BITS_PART_LOG ? 1 << (sbits - MSM_BITS_PART_LOG) : 1;
+}
+
+int MsmScratch::alloc(const MsmPlan* plans, int count, bool need_g2) {
   // capacity = max over the plans that will actually run on this scratch
-  uint64_t ent = 1, bk = 1, tk = 1;
+  uint64_t ent = 1, bk = 1, tk = 1, vp = 1;
   for (int i = 0; i < count; i++) {
-    if (sizes[i] == 0) continue;
-    MsmPlan p = MsmPlan::make((uint32_t)sizes[i]);
-    ent = std::max<uint64_t>(ent, sizes[i] * p.W);
+    const MsmPlan& p = plans[i];
+    if (p.n == 0) continue;
+    ent = std::max<uint64_t>(ent, (uint64_t)p.n * p.W);
     bk = std::max<uint64_t>(bk, p.nbuckets());
-    tk = std::max<uint64_t>(tk, ((sizes[i] * p.W) >> p.task_log) + p.nbuckets() + 2);
+    tk = std::max<uint64_t>(tk, (((uint64_t)p.n * p.W) >> p.task_log) + p.nbuckets() + 2);
+    vp = std::max<uint64_t>(vp, (uint64_t)p.wred() * (p.c - p.seg_log) * bits_parts(p));
   }
   cap_entries = ent;
   cap_buckets = bk;
@@ -54,7 +82,7 @@ int MsmScratch::alloc(const uint64_t* sizes, int count, bool need_g2) {
   if (cudaMalloc(&buckets, bk * psz) != cudaSuccess) return -1;
   if (cudaMalloc(&segR, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment weighted sums (K >= 2)
   if (cudaMalloc(&segS, (bk / 2 + 1) * psz) != cudaSuccess) return -1;  // per-segment plain sums
-  winsum = nullptr;
+  if (cudaMalloc(&winsum, vp * psz) != cudaSuccess) return -1;
   // task decomposition of the bucket runs (load balancing under skewed digits)
   cap_tasks = tk + 1;
   if (cudaMalloc(&ntasks, (bk + 1) * 4) != cudaSuccess) return -1;
@@ -85,7 +113,7 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int 
 // SCATTER=false: histogram.  SCATTER=true: place entries using cursor (pre-loaded with offsets).
 template <bool SCATTER>
 __global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restrict__ map,
-                         uint32_t n, int c, int W, uint32_t B, uint32_t* __restrict__ counter,
+                         uint32_t n, int c, int W, uint32_t B, bool table, uint32_t* __restrict__ counter,
                          uint32_t* __restrict__ sorted) {
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     Fr s = from_mont(scalars[map ? map[i] : i]);
@@ -101,9 +129,10 @@ __global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restr
         carry = 0;
       }
       if (mag != 0) {
-        uint32_t bucket = (uint32_t)w * B + mag - 1;
+        // table mode: every window shares one bucket set and digit w selects the point 2^(c w) P_i
+        uint32_t bucket = (table ? 0u : (uint32_t)w * B) + mag - 1;
         uint32_t pos = atomicAdd(&counter[bucket], 1u);
-        if (SCATTER) sorted[pos] = i | (neg << 31);
+        if (SCATTER) sorted[pos] = (table ? (uint32_t)w * n + i : i) | (neg << 31);
       }
     }
   }
@@ -295,25 +324,30 @@ k_bucket_segments(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, int seg_l
   segS[s] = run;
 }
 
-// grid = W * (1 + sbits) CTAs, sbits = bits of the segment index.  CTA (w, 0): V[c w] = sum_s R_s;
-// CTA (w, 1 + k): V[c w + seg_log + k] = sum of S_s over segments whose index has bit k set.
+// grid = wred * (1 + sbits) * parts CTAs, sbits = bits of the segment index.  Job (w, 0): V[c w] = sum_s R_s;
+// job (w, 1 + k): V[c w + seg_log + k] = sum of S_s over segments whose index has bit k set.  A job's
+// segment range is cut into `parts` CTAs (window-table plans have one window of up to 2^18 segments);
+// with parts > 1 the CTA sums go to Vpart and k_fold_parts adds them up.
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_segment_bits(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ segS, int c, int seg_log,
-               int sbits, XYZZ<F>* __restrict__ V) {
+               int sbits, int parts, XYZZ<F>* __restrict__ V, XYZZ<F>* __restrict__ Vpart) {
   __shared__ XYZZ<F> sh[THREADS];
   const int per_w = 1 + sbits;
-  const int w = blockIdx.x / per_w, which = blockIdx.x % per_w;
+  const int job = blockIdx.x / parts, part = blockIdx.x % parts;
+  const int w = job / per_w, which = job % per_w;
   const uint32_t segs = 1u << sbits;
   XYZZ<F> acc = XYZZ<F>::inf();
   if (which == 0) {
     const XYZZ<F>* R = segR + (uint64_t)w * segs;
-    for (uint32_t s = threadIdx.x; s < segs; s += THREADS) acc = add_cold(acc, R[s]);
+    const uint32_t len = segs / parts, lo = part * len;
+    for (uint32_t s = lo + threadIdx.x; s < lo + len; s += THREADS) acc = add_cold(acc, R[s]);
   } else {
     const int k = which - 1;
     const XYZZ<F>* S = segS + (uint64_t)w * segs;
     const uint32_t low_mask = (1u << k) - 1;
-    for (uint32_t t = threadIdx.x; t < (segs >> 1); t += THREADS) {
+    const uint32_t len = (segs >> 1) / parts, lo = part * len;
+    for (uint32_t t = lo + threadIdx.x; t < lo + len; t += THREADS) {
       const uint32_t sidx = ((t & ~low_mask) << 1) | (1u << k) | (t & low_mask);  // insert a 1 at bit k
       acc = add_cold(acc, S[sidx]);
     }
@@ -324,7 +358,83 @@ k_segment_bits(const XYZZ<F>* __restrict__ segR, const XYZZ<F>* __restrict__ seg
     if ((int)threadIdx.x < st) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + st]);
     __syncthreads();
   }
+  if (threadIdx.x == 0) {
+    if (parts == 1) V[c * w + (which == 0 ? 0 : seg_log + which - 1)] = sh[0];
+    else Vpart[(uint64_t)job * parts + part] = sh[0];
+  }
+}
+
+// one warp per job: V[...] = sum of the job's `parts` partial sums
+template <class F>
+__global__ void __launch_bounds__(32)
+k_fold_parts(const XYZZ<F>* __restrict__ Vpart, int c, int seg_log, int sbits, int parts, XYZZ<F>* __restrict__ V) {
+  __shared__ XYZZ<F> sh[32];
+  const int per_w = 1 + sbits;
+  const int job = blockIdx.x, w = job / per_w, which = job % per_w;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int j = threadIdx.x; j < parts; j += 32) acc = add_cold(acc, Vpart[(uint64_t)job * parts + j]);
+  sh[threadIdx.x] = acc;
+  __syncwarp();
+  for (int st = 16; st > 0; st >>= 1) {
+    if ((int)threadIdx.x < st) sh[threadIdx.x] = add_cold(sh[threadIdx.x], sh[threadIdx.x + st]);
+    __syncwarp();
+  }
   if (threadIdx.x == 0) V[c * w + (which == 0 ? 0 : seg_log + which - 1)] = sh[0];
+}
+
+// ------------------------------------------------------------ window table ---
+// tab[w*n + i] = 2^(c w) * tab[i].  One thread per base: c doublings per window in XYZZ while tracking
+// Z (zz = Z^2, zzz = Z^3: each doubling multiplies Z by 2Y), (X, Y) parked in the output slot, then one
+// shared inversion for the thread's W-1 points (Montgomery's trick) and x = X/Z^2, y = Y/Z^3 in place.
+constexpr int MSM_MAX_W = 64;
+template <class F>
+__global__ void __launch_bounds__(128)
+k_build_window_table(Affine<F>* __restrict__ tab, uint32_t n, int c, int W) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Affine<F> p = tab[i];
+  F zs[MSM_MAX_W];  // Z of window w (one() for points at infinity, which are stored as such)
+  F X = p.x, Y = p.y, Z = F::one();
+  bool inf = p.is_inf();
+  for (int w = 1; w < W; w++) {
+    for (int j = 0; j < c && !inf; j++) {
+      if (Y.is_zero()) { inf = true; break; }
+      // dbl-2008-s-1 with zz = Z^2, zzz = Z^3 implicit
+      F U = dbl(Y);
+      F V = sqr(U);
+      F Wc = mul(U, V);
+      F S = mul(X, V);
+      F X2 = sqr(X);
+      F M = add(dbl(X2), X2);
+      F X3 = sub(sqr(M), dbl(S));
+      Y = sub(mul(M, sub(S, X3)), mul(Wc, Y));
+      X = X3;
+      Z = mul(Z, U);
+    }
+    if (inf) {
+      tab[(uint64_t)w * n + i] = Affine<F>::inf();
+      zs[w] = F::one();
+    } else {
+      tab[(uint64_t)w * n + i] = Affine<F>{X, Y};
+      zs[w] = Z;
+    }
+  }
+  if (W < 2) return;
+  // prefix products pr[w] = zs[1] * ... * zs[w], kept in zs by a second array
+  F pr[MSM_MAX_W];
+  pr[1] = zs[1];
+  for (int w = 2; w < W; w++) pr[w] = mul(pr[w - 1], zs[w]);
+  F iv = inv_cold(pr[W - 1]);
+  for (int w = W - 1; w >= 1; w--) {
+    const F iz = w > 1 ? mul(iv, pr[w - 1]) : iv;  // 1 / zs[w]
+    iv = mul(iv, zs[w]);
+    Affine<F> q = tab[(uint64_t)w * n + i];
+    if (q.is_inf()) continue;
+    const F iz2 = sqr(iz);
+    q.x = mul(q.x, iz2);
+    q.y = mul(q.y, mul(iz2, iz));
+    tab[(uint64_t)w * n + i] = q;
+  }
 }
 
 // ----------------------------------------------------------------- driver ---
@@ -333,7 +443,7 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
                    const MsmPlan& p, MsmScratch& s, XYZZ<F>* out, bool reuse_sort,
                    cudaStream_t st) {
   const uint32_t nb = p.nbuckets();
-  if (p.W > 64) return -1;
+  if (p.W > MSM_MAX_W || bits_parts(p) > 1024) return -1;
   if (p.n == 0) {
     cudaMemsetAsync(out, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
     return 0;
@@ -342,12 +452,12 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   if (!reuse_sort) {
     cudaMemsetAsync(s.hist, 0, (size_t)(nb + 1) * 4, st);
     const unsigned dg = (unsigned)std::min<uint64_t>((p.n + 255) / 256, 148 * 16);
-    k_digits<false><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, s.hist, nullptr);
+    k_digits<false><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, s.hist, nullptr);
     const unsigned sb = (nb + 1 + 1023) / 1024;
     k_scan_block<<<sb, 1024, 0, st>>>(s.hist, s.offsets, s.blocksums, nb + 1);
     k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb);
     k_scan_add<<<sb, 1024, 0, st>>>(s.offsets, s.cursor, s.blocksums, nb + 1);
-    k_digits<true><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, s.cursor, s.sorted);
+    k_digits<true><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, s.cursor, s.sorted);
   }
   XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(s.buckets);
   XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
@@ -368,9 +478,16 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   const uint32_t nsegs = nb >> p.seg_log;
   XYZZ<F>* V = out;  // MSM_VBITS entries
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
+  const int parts = bits_parts(p);
+  const int jobs = p.wred() * (1 + sbits);
   cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
   k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
-  k_segment_bits<F, BT><<<p.W * (1 + sbits), BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, V);
+  k_segment_bits<F, BT><<<jobs * parts, BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, parts, V,
+                                                    reinterpret_cast<XYZZ<F>*>(s.winsum));
+  if (parts > 1) {
+    k_fold_parts<F><<<jobs, 32, 0, st>>>(reinterpret_cast<XYZZ<F>*>(s.winsum), p.c, p.seg_log, sbits, parts, V);
+    count_launch(1);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
@@ -382,5 +499,16 @@ int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const 
            MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st) {
   return msm_run<Fq2>(bases, scalars, map, plan, s, out, reuse_sort, st);
 }
+
+template <class F>
+static int build_table(Affine<F>* tab, const MsmPlan& p, cudaStream_t st) {
+  if (!p.table || p.n == 0 || p.W < 2) return 0;
+  if (p.W > MSM_MAX_W) return -1;
+  k_build_window_table<F><<<(p.n + 127) / 128, 128, 0, st>>>(tab, p.n, p.c, p.W);
+  count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+int msm_build_table_g1(G1Affine* tab, const MsmPlan& plan, cudaStream_t st) { return build_table<Fq>(tab, plan, st); }
+int msm_build_table_g2(G2Affine* tab, const MsmPlan& plan, cudaStream_t st) { return build_table<Fq2>(tab, plan, st); }
 
 }  // namespace fb

@@ -37,13 +37,21 @@ constexpr int MSM_VBITS = 288;            // >= W*c for every plan (255 + c - 1 
 struct MsmPlan {
   uint32_t n = 0;       // number of (scalar, base) pairs
   int c = 0;            // window bits
-  int W = 0;            // number of windows, W*c >= 255
+  int W = 0;            // number of windows (digits per scalar), W*c >= 255
   uint32_t B = 0;       // buckets per window = 2^(c-1)
   int seg_log = 0;      // buckets per reduce segment = 2^seg_log
   int task_log = 4;     // entries per accumulation task = 2^task_log
-  static MsmPlan make(uint32_t n);
-  uint32_t nbuckets() const { return (uint32_t)W * B; }
+  // Window-table mode: the base array holds 2^(c w) P_i at index w*n + i for every window w (built once
+  // per key, k_build_window_table), so digit w of scalar i is just one more point for the ONE shared
+  // bucket set.  The reduction then costs 2^(c-1) buckets instead of W * 2^(c-1), which lets c grow by
+  // ~4 bits: 15 -> 12 digits per scalar at n = 2^24.  Costs W x the base memory (HBM is 180 GB).
+  bool table = false;
+  static MsmPlan make(uint32_t n, bool table = false);
+  int wred() const { return table ? 1 : W; }                   // bucket sets to reduce
+  uint32_t nbuckets() const { return (uint32_t)wred() * B; }
   uint32_t nsegs() const { return nbuckets() >> seg_log; }
+  int vbits() const { return wred() * c; }                     // V entries the host Horner consumes
+  uint64_t table_points() const { return table ? (uint64_t)n * W : n; }
 };
 
 // Scratch shared by consecutive MSMs on one stream (sized for the largest plan).
@@ -56,13 +64,13 @@ struct MsmScratch {
   void* buckets = nullptr;      // [nbuckets] XYZZ (sized for G2)
   void* segR = nullptr;         // [nsegs] XYZZ: per-segment weighted sums
   void* segS = nullptr;         // [nsegs] XYZZ: per-segment plain sums
-  void* winsum = nullptr;       // [1024] XYZZ: V[p] (first 288) and the doubling-tree scratch
+  void* winsum = nullptr;       // [(1 + sbits) * wred * parts] XYZZ: per-CTA partial bit sums (k_segment_bits)
   uint32_t* ntasks = nullptr;   // [nbuckets + 1]
   uint32_t* task_off = nullptr; // [nbuckets + 1]
   void* partials = nullptr;     // [cap_tasks] XYZZ
   uint32_t* heavy = nullptr;    // [0] = count, then bucket ids
   size_t cap_entries = 0, cap_buckets = 0, cap_tasks = 0;
-  int alloc(const uint64_t* sizes, int count, bool need_g2);
+  int alloc(const MsmPlan* plans, int count, bool need_g2);
   void release();
 };
 
@@ -74,6 +82,9 @@ int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const 
            MsmScratch& s, G1XYZZ* out, bool reuse_sort, cudaStream_t st);
 int msm_g2(const G2Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,
            MsmScratch& s, G2XYZZ* out, bool reuse_sort, cudaStream_t st);
+// Fill tab[w*n + i] = 2^(c w) tab[i] for w = 1..W-1 (tab[0..n) holds the bases); plan.table must be set.
+int msm_build_table_g1(G1Affine* tab, const MsmPlan& plan, cudaStream_t st);
+int msm_build_table_g2(G2Affine* tab, const MsmPlan& plan, cudaStream_t st);
 
 // Host side of step 6: Horner over the bit sums, on 64-bit-limb host arithmetic.
 template <class HF, class DF>

@@ -300,14 +300,18 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   const size_t psz = group == 1 ? 64 : 128;
   void *dbases, *dres;
   Fr* dsc;
-  FB_CUDA(cudaMalloc(&dbases, n * psz));
+  MsmPlan plan = MsmPlan::make((uint32_t)n, g_msm_tables == 1);  // fb_set_msm_tables(1) selects window tables
+  FB_CUDA(cudaMalloc(&dbases, plan.table_points() * psz));
   FB_CUDA(cudaMalloc(&dsc, n * 32));
   FB_CUDA(cudaMalloc(&dres, sizeof(G2XYZZ) * MSM_VBITS));
   FB_CUDA(cudaMemcpyAsync(dbases, bases_raw, n * psz, cudaMemcpyHostToDevice, st));
   FB_CUDA(cudaMemcpyAsync(dsc, scalars, n * 32, cudaMemcpyHostToDevice, st));
-  MsmPlan plan = MsmPlan::make((uint32_t)n);
+  if ((group == 1 ? msm_build_table_g1((G1Affine*)dbases, plan, st) : msm_build_table_g2((G2Affine*)dbases, plan, st)) != 0) {
+    set_error("msm window table build failed");
+    return FB_ERR_CUDA;
+  }
   MsmScratch scr;
-  if (scr.alloc(&n, 1, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
+  if (scr.alloc(&plan, 1, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
   std::vector<G2XYZZ> hres(MSM_VBITS);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -315,7 +319,7 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   if (reps < 1) reps = 1;
   float best = 1e30f;
   int rc = 0;
-  const int nbits = plan.W * plan.c;
+  const int nbits = plan.vbits();
   for (int rep = 0; rep < reps && !rc; rep++) {
     // timed: digits + sort + accumulate + reduce on the device, then the Horner tail on the host
     auto h0 = std::chrono::steady_clock::now();

@@ -161,6 +161,10 @@ uint64_t fb_launch_count(void);
 /* 1: run every kernel of a prove on one stream (per-kernel timings are then undisturbed);
  * 0 (default): the witness-only MSMs run on side streams beside the H pipeline */
 void fb_set_serial(int on);
+/* MSM window tables (2^(c w) P for every window w, W x the base memory, fewer digits per scalar):
+ * -1 auto (default: on when they fit in free HBM with headroom), 0 off, 1 on.  Applies to keys loaded
+ * afterwards and to fb_test_msm. */
+void fb_set_msm_tables(int mode);
 void fb_kernel_stats_enable(int on);
 void fb_kernel_stats_reset(void);
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms);

@@ -12,6 +12,16 @@ from tests.util import fr_np, random_g1, random_g2
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["plain", "window_tables"], autouse=True)
+def msm_tables(request):
+    """Every MSM test runs twice: plain per-window buckets and the window-table mode (2^(c w) P tables,
+    one shared bucket set)."""
+    import fawkes_crypto_b200 as fb
+    fb.native.lib.fb_set_msm_tables(request.param)
+    yield request.param
+    fb.native.lib.fb_set_msm_tables(-1)
+
+
 def gpu_msm(ctx, group, bases, scalars):
     import fawkes_crypto_b200 as fb
     enc = codec.g1_raw if group == 1 else codec.g2_raw

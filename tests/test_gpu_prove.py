@@ -18,9 +18,11 @@ def oracle_case(n_rows, seed):
     return gates, inp, aux, td, r, s, P
 
 
+@pytest.mark.parametrize("tables", [0, 1], ids=["plain_msm", "window_tables"])
 @pytest.mark.parametrize("n_rows", [3, 17, 64, 700])
-def test_prove_matches_oracle_bytes(ctx, n_rows):
+def test_prove_matches_oracle_bytes(ctx, n_rows, tables):
     import fawkes_crypto_b200 as fb
+    fb.native.lib.fb_set_msm_tables(tables)   # keys loaded below use / do not use the MSM window tables
     seed = synth.SEED_BASE + 100 + n_rows
     gates, inp, aux, td, r, s, P = oracle_case(n_rows, seed)
     ref_proof, ref_h = og.prove(P, gates, inp, aux, r, s, return_h=True)
@@ -39,6 +41,7 @@ def test_prove_matches_oracle_bytes(ctx, n_rows):
     bad = fr_np([(inp[1] + 1) % bn.R])
     assert not fb.verify(params.get_vk(), proof, bad)
     params.unload()
+    fb.native.lib.fb_set_msm_tables(-1)
 
 
 @pytest.mark.parametrize("n_rows", [5, 64, 300])

@@ -1,20 +1,37 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel.
+
+With --last-prove only the launches of the last prove in the file are counted (a prove starts at its
+first k_spmv launch: R1CS evaluation is the first thing a prove does on the main stream in the serial
+schedule; the witness-only MSMs that precede it on the same stream in that schedule are attributed by
+walking back to the previous prove's end)."""
 import collections
 import csv
 import sys
 
-rows = list(csv.reader(l for l in open(sys.argv[1]) if l.startswith('"')))
+path = sys.argv[1]
+rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
 hdr = rows[0]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+rows = rows[1:]
+if "--last-prove" in sys.argv:
+    # a prove = everything between two h2d-separated groups; we split on the witness MSM's first k_digits<0>
+    # that follows a k_fold_parts/k_segment_bits of the H MSM, i.e. on groups of 3 consecutive k_spmv
+    spmv = [i for i, r in enumerate(rows) if r[ki].startswith("k_spmv")]
+    groups = [spmv[i] for i in range(0, len(spmv), 3)]
+    if len(groups) >= 2:
+        per = groups[-1] - groups[-2]
+        end = len(rows)
+        # the prove's launches: same count as the distance between two proves, ending at the file end
+        rows = rows[end - per:]
 agg = collections.OrderedDict()
 tot = 0.0
-for r in rows[1:]:
+for r in rows:
     k = r[ki][:70]
     v = float(r[vi].replace(",", ""))
     agg.setdefault(k, [0, 0.0])
     agg[k][0] += 1
     agg[k][1] += v
     tot += v
-print(f"total {tot/1e6:.3f} ms over {len(rows)-1} launches")
+print(f"total {tot/1e6:.3f} ms over {len(rows)} launches")
 for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{c:5d} {t/1e6:12.3f} ms {100*t/tot:6.1f}%  {k}")

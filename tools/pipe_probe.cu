@@ -199,8 +199,7 @@ __global__ void k_check(uint32_t* bad, int n) {
     if (r == 7) { c = a; d = b; }
     F ref = mul_c(a, b);
     if (mul_v2(a, b) != ref || mul_ptx(a, b) != ref) atomicAdd(&bad[0], 1u);
-    if (mul_v3(a, b) != ref) atomicAdd(&bad[4], 1u);
-    if (dot2_v3(a, b, pneg_raw(c), d) != sub_c(mul_c(a, b), mul_c(c, d))) atomicAdd(&bad[5], 1u);
+
     if (sqr_ptx(a) != mul_c(a, a)) atomicAdd(&bad[1], 1u);
     if (msub2(a, b, c, d) != sub_c(mul_c(a, b), mul_c(c, d))) atomicAdd(&bad[2], 1u);
     Fq2 x{Fq{}, Fq{}}, y{Fq{}, Fq{}};
@@ -226,8 +225,7 @@ __global__ void k_rate(Fq* out, int iters) {
     if (V == 0) { x = mul_v2(x, y); y = mul_v2(y, x); }
     else if (V == 1) { x = sqr_ptx(x); y = sqr_ptx(y); }
     else if (V == 2) { x = msub2(x, y, z, x); y = msub2(y, x, z, y); }
-    else if (V == 4) { x = mul_v3(x, y); y = mul_v3(y, x); }
-    else if (V == 5) { x = dot2_v3(x, y, z, x); y = dot2_v3(y, x, z, y); }
+
     else { x = mul_ptx(x, y); y = mul_ptx(y, x); }
   }
   if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
@@ -250,6 +248,58 @@ template <class F>
 __global__ void k_rate_madd(const Affine<F>* pts, XYZZ<F>* out, int iters) {
   XYZZ<F> acc = XYZZ<F>::from_affine(pts[threadIdx.x & 15]);
   for (int i = 0; i < iters; i++) acc = add_mixed(acc, pts[16 + ((i + threadIdx.x) & 15)]);
+  if (acc.x.is_zero()) out[0] = acc;
+}
+// same mixed add with the field multiplies as real calls (small loop body: instruction-cache friendly)
+__device__ __noinline__ Fq mul_call(Fq a, Fq b) { return mul(a, b); }
+__device__ __noinline__ Fq sqr_call(Fq a) { return sqr(a); }
+__device__ __noinline__ Fq msub2_call(Fq a, Fq b, Fq c, Fq d) { return msub2(a, b, c, d); }
+__device__ __forceinline__ G1XYZZ add_mixed_calls(const G1XYZZ& a, const G1Affine& q) {
+  if (q.is_inf()) return a;
+  if (a.is_inf()) return {q.x, q.y, Fq::one(), Fq::one()};
+  Fq U2 = mul_call(q.x, a.zz);
+  Fq S2 = mul_call(q.y, a.zzz);
+  Fq Pp = sub(U2, a.x);
+  Fq R = sub(S2, a.y);
+  if (Pp.is_zero()) {
+    if (R.is_zero()) return dbl_affine(q);
+    return G1XYZZ::inf();
+  }
+  Fq PP = sqr_call(Pp);
+  Fq PPP = mul_call(Pp, PP);
+  Fq Q = mul_call(a.x, PP);
+  Fq X3 = sub(sub(sqr_call(R), PPP), dbl(Q));
+  Fq Y3 = msub2_call(R, sub(Q, X3), a.y, PPP);
+  return {X3, Y3, mul_call(a.zz, PP), mul_call(a.zzz, PPP)};
+}
+__global__ void k_rate_madd_calls(const G1Affine* pts, G1XYZZ* out, int iters) {
+  G1XYZZ acc = G1XYZZ::from_affine(pts[threadIdx.x & 15]);
+  for (int i = 0; i < iters; i++) acc = add_mixed_calls(acc, pts[16 + ((i + threadIdx.x) & 15)]);
+  if (acc.x.is_zero()) out[0] = acc;
+}
+__device__ __noinline__ Fq2 mul2_call(Fq2 a, Fq2 b) { return mul(a, b); }
+__device__ __noinline__ Fq2 sqr2_call(Fq2 a) { return sqr(a); }
+__device__ __forceinline__ G2XYZZ add_mixed_calls2(const G2XYZZ& a, const G2Affine& q) {
+  if (q.is_inf()) return a;
+  if (a.is_inf()) return {q.x, q.y, Fq2::one(), Fq2::one()};
+  Fq2 U2 = mul2_call(q.x, a.zz);
+  Fq2 S2 = mul2_call(q.y, a.zzz);
+  Fq2 Pp = sub(U2, a.x);
+  Fq2 R = sub(S2, a.y);
+  if (Pp.is_zero()) {
+    if (R.is_zero()) return dbl_affine(q);
+    return G2XYZZ::inf();
+  }
+  Fq2 PP = sqr2_call(Pp);
+  Fq2 PPP = mul2_call(Pp, PP);
+  Fq2 Q = mul2_call(a.x, PP);
+  Fq2 X3 = sub(sub(sqr2_call(R), PPP), dbl(Q));
+  Fq2 Y3 = sub(mul2_call(R, sub(Q, X3)), mul2_call(a.y, PPP));
+  return {X3, Y3, mul2_call(a.zz, PP), mul2_call(a.zzz, PPP)};
+}
+__global__ void k_rate_madd_calls2(const G2Affine* pts, G2XYZZ* out, int iters) {
+  G2XYZZ acc = G2XYZZ::from_affine(pts[threadIdx.x & 15]);
+  for (int i = 0; i < iters; i++) acc = add_mixed_calls2(acc, pts[16 + ((i + threadIdx.x) & 15)]);
   if (acc.x.is_zero()) out[0] = acc;
 }
 template <class F>
@@ -327,8 +377,6 @@ int main(int argc, char** argv) {
   M muls[] = {
     {"mul_ptx", [](int t, int b, int it, void* d) { k_rate<3><<<b, t>>>((Fq*)d, it); }, 2},
     {"mul_v2", [](int t, int b, int it, void* d) { k_rate<0><<<b, t>>>((Fq*)d, it); }, 2},
-    {"mul_v3 (karatsuba)", [](int t, int b, int it, void* d) { k_rate<4><<<b, t>>>((Fq*)d, it); }, 2},
-    {"dot2_v3 (karatsuba)", [](int t, int b, int it, void* d) { k_rate<5><<<b, t>>>((Fq*)d, it); }, 2},
     {"sqr_ptx", [](int t, int b, int it, void* d) { k_rate<1><<<b, t>>>((Fq*)d, it); }, 2},
     {"msub2 (2 products)", [](int t, int b, int it, void* d) { k_rate<2><<<b, t>>>((Fq*)d, it); }, 2},
     {"fq2 mul lazy", [](int t, int b, int it, void* d) { k_rate2<0><<<b, t>>>((Fq2*)d, it); }, 2},
@@ -352,11 +400,43 @@ int main(int argc, char** argv) {
     cudaDeviceSynchronize();
     static G1Affine* spts; spts = pts;
     auto fn = [](int t, int b, int it, void* d) { k_rate_madd<Fq><<<b, t>>>(spts, (G1XYZZ*)d, it); };
+    auto fn2 = [](int t, int b, int it, void* d) { k_rate_madd_calls<<<b, t>>>(spts, (G1XYZZ*)d, it); };
+    for (int cfg = 0; cfg < 3; cfg++) {
+      int threads = 128, bps = cfg == 0 ? 3 : (cfg == 1 ? 4 : 6), iters = 1 << 9;
+      double t = run(fn2, threads, bps, iters, d);
+      double adds_s = (double)iters * threads * bps * 148 / t;
+      printf("G1 add_mixed (calls)   warps/SMSP=%4.0f  %.3e adds/s   %.0f cycles per warp-add per SMSP (%s)\n",
+             threads * bps / 128.0, adds_s, 148.0 * 4 * 32 * f / adds_s, cudaGetErrorString(cudaGetLastError()));
+    }
     for (int cfg = 0; cfg < 2; cfg++) {
       int threads = 128, bps = cfg == 0 ? 3 : 4, iters = 1 << 9;
       double t = run(fn, threads, bps, iters, d);
       double adds_s = (double)iters * threads * bps * 148 / t;
       printf("G1 add_mixed           warps/SMSP=%4.0f  %.3e adds/s   %.0f cycles per warp-add per SMSP (%s)\n",
+             threads * bps / 128.0, adds_s, 148.0 * 4 * 32 * f / adds_s, cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  {  // mixed-add rate, G2 (arbitrary coordinates: the formulas do not care about curve membership)
+    G2Affine* pts = (G2Affine*)((char*)d + 16384);
+    G2Affine g; g.x = Fq2{Fq::one(), Fq::r2()}; g.y = Fq2{Fq::r2(), Fq::one()};
+    cudaMemcpy(pts, &g, sizeof(g), cudaMemcpyHostToDevice);
+    k_make_pts<Fq2><<<1, 1>>>(pts, Fq2::zero());
+    cudaDeviceSynchronize();
+    static G2Affine* spts2; spts2 = pts;
+    auto fn = [](int t, int b, int it, void* d) { k_rate_madd<Fq2><<<b, t>>>(spts2, (G2XYZZ*)d, it); };
+    auto fn2 = [](int t, int b, int it, void* d) { k_rate_madd_calls2<<<b, t>>>(spts2, (G2XYZZ*)d, it); };
+    for (int cfg = 0; cfg < 4; cfg++) {
+      int threads = 128, bps = cfg + 1, iters = 1 << 8;
+      double t = run(fn2, threads, bps, iters, d);
+      double adds_s = (double)iters * threads * bps * 148 / t;
+      printf("G2 add_mixed (calls)   warps/SMSP=%4.1f  %.3e adds/s   %.0f cycles per warp-add per SMSP (%s)\n",
+             threads * bps / 128.0, adds_s, 148.0 * 4 * 32 * f / adds_s, cudaGetErrorString(cudaGetLastError()));
+    }
+    for (int cfg = 0; cfg < 3; cfg++) {
+      int threads = cfg == 2 ? 64 : 128, bps = cfg == 0 ? 1 : 2, iters = 1 << 8;
+      double t = run(fn, threads, bps, iters, d);
+      double adds_s = (double)iters * threads * bps * 148 / t;
+      printf("G2 add_mixed           warps/SMSP=%4.1f  %.3e adds/s   %.0f cycles per warp-add per SMSP (%s)\n",
              threads * bps / 128.0, adds_s, 148.0 * 4 * 32 * f / adds_s, cudaGetErrorString(cudaGetLastError()));
     }
   }
