@@ -9,6 +9,7 @@
 #include "ff.cuh"
 #include "ff29.cuh"
 #include "ec.cuh"
+#include "ff52.cuh"
 
 using namespace fb;
 
@@ -215,6 +216,52 @@ __global__ void k_check(uint32_t* bad, int n) {
 #endif
 }
 
+// 52-bit FP64 multiplier vs the portable reference: bad[6] mul52, bad[7] add/sub52
+template <class F, class C52>
+__global__ void k_check52(uint32_t* bad, int n) {
+#if defined(__CUDA_ARCH__)
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t st = 0x9e3779b9u * (i + 7) + 999u;
+  for (int r = 0; r < 24; r++) {
+    F a = r < 5 ? edge<F>(r) : rnd<F>(st), b = (r % 7 == 3) ? edge<F>((r + i) % 5) : rnd<F>(st);
+    if (r == 4 || ((r % 7 == 3) && ((r + i) % 5) == 4)) continue;  // edge 4 is >= p: not a field element
+    F ref = mul_c(a, b);
+    F52<C52> A = to52<C52, 4>(a), B = to52<C52, 0>(b);
+    F got = from52_raw(mul52(A, B));
+    ptx::cond_sub<typename F::Cfg>(got.v);
+    if (got != ref) atomicAdd(&bad[6], 1u);
+    // chain: (a*b)*b through the 2^260 form, back through from52_std
+    F52<C52> A2 = mul52(to52<C52, 4>(a), to52<C52, 4>(b));  // (ab) 2^260
+    F52<C52> A3 = mul52(A2, to52<C52, 4>(b));
+    if (from52_std(A3) != mul_c(ref, b)) atomicAdd(&bad[6], 1u);
+    F d = from52_raw(sub52<C52, 2>(to52<C52, 0>(a), to52<C52, 0>(b)));
+    ptx::cond_sub<typename F::Cfg>(d.v); ptx::cond_sub<typename F::Cfg>(d.v);
+    if (d != sub_c(a, b)) atomicAdd(&bad[7], 1u);
+    F e = from52_raw(add52(to52<C52, 0>(a), to52<C52, 0>(b)));
+    ptx::cond_sub<typename F::Cfg>(e.v);
+    if (e != add_c(a, b)) atomicAdd(&bad[7], 1u);
+  }
+#endif
+}
+template <int V>
+__global__ void k_rate52(Fq* out, int iters) {
+#if defined(__CUDA_ARCH__)
+  Fq x0 = Fq::one(), y0 = Fq::r2();
+  x0.v[0] += threadIdx.x; y0.v[1] ^= blockIdx.x + 3 * threadIdx.x;
+  const int warp = threadIdx.x >> 5;
+  if (V == 0 || (V == 2 && (warp & 1))) {
+    Fq52 x = to52<Fq52Cfg, 4>(x0), y = to52<Fq52Cfg, 4>(y0);
+    for (int i = 0; i < iters; i++) { x = mul52(x, y); y = mul52(y, x); }
+    if (x.l[0] == 0x12345678u && y.l[3] == 0x9abcdef0u) out[0] = from52_raw(x);
+  } else {
+    Fq x = x0, y = y0;
+    for (int i = 0; i < iters; i++) { x = mul_v2(x, y); y = mul_v2(y, x); }
+    if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
+  }
+#endif
+}
+
 // throughput kernels: V = 0 mul_v2, 1 sqr_ptx, 2 msub2, 3 mul_ptx
 template <int V>
 __global__ void k_rate(Fq* out, int iters) {
@@ -371,20 +418,25 @@ int main(int argc, char** argv) {
   cudaMemset(bad, 0, 64);
   k_check<Fq><<<64, 128>>>(bad, 64 * 128);
   k_check<Fr><<<64, 128>>>(bad, 64 * 128);
+  k_check52<Fq, Fq52Cfg><<<64, 128>>>(bad, 64 * 128);
+  k_check52<Fr, Fr52Cfg><<<64, 128>>>(bad, 64 * 128);
   uint32_t hb[8]; cudaMemcpy(hb, bad, 32, cudaMemcpyDeviceToHost);
+  printf("mismatches: mul52 %u addsub52 %u\n", hb[6], hb[7]);
   printf("mismatches: mul %u sqr %u msub2 %u fq2mul %u mul_v3 %u dot2_v3 %u (%s)\n", hb[0], hb[1], hb[2], hb[3], hb[4], hb[5], cudaGetErrorString(cudaGetLastError()));
   struct M { const char* name; void (*fn)(int, int, int, void*); int per; };
   M muls[] = {
     {"mul_ptx", [](int t, int b, int it, void* d) { k_rate<3><<<b, t>>>((Fq*)d, it); }, 2},
     {"mul_v2", [](int t, int b, int it, void* d) { k_rate<0><<<b, t>>>((Fq*)d, it); }, 2},
+    {"mul52 (FP64 pipe)", [](int t, int b, int it, void* d) { k_rate52<0><<<b, t>>>((Fq*)d, it); }, 2},
+    {"mixed mul52 | mul_v2 warps", [](int t, int b, int it, void* d) { k_rate52<2><<<b, t>>>((Fq*)d, it); }, 2},
     {"sqr_ptx", [](int t, int b, int it, void* d) { k_rate<1><<<b, t>>>((Fq*)d, it); }, 2},
     {"msub2 (2 products)", [](int t, int b, int it, void* d) { k_rate<2><<<b, t>>>((Fq*)d, it); }, 2},
     {"fq2 mul lazy", [](int t, int b, int it, void* d) { k_rate2<0><<<b, t>>>((Fq2*)d, it); }, 2},
     {"fq2 mul old", [](int t, int b, int it, void* d) { k_rate2<1><<<b, t>>>((Fq2*)d, it); }, 2},
   };
   for (auto& m : muls) {
-    for (int cfg = 0; cfg < 2; cfg++) {
-      int threads = cfg == 0 ? 128 : 256, bps = 4, iters = 1 << 11;
+    for (int cfg = 0; cfg < 3; cfg++) {
+      int threads = cfg == 0 ? 128 : 256, bps = cfg == 2 ? 8 : 4, iters = 1 << 11;
       double t = run(m.fn, threads, bps, iters, d);
       double warps_per_smsp = threads * bps / 128.0;
       double ops_s = (double)iters * m.per * threads * bps * 148 / t;
