@@ -46,10 +46,14 @@ for lg in logs:
         fb.native.check(lib.fb_test_fixed_base(ctx.handle, group, k.ctypes.data, n, bases.ctypes.data))
         out[f"fixed_base_g{group}_s_2^{lg}"] = time.time() - t
         res = np.zeros(psz, dtype=np.uint8)
-        fb.native.check(lib.fb_test_msm(ctx.handle, group, bases.ctypes.data, a.ctypes.data, n, res.ctypes.data, 3, C.byref(ms)))
-        out[f"msm_g{group}_ms_2^{lg}"] = ms.value
-        out[f"msm_g{group}_mpts_2^{lg}"] = n / ms.value / 1e3
-        print(lg, "msm g", group, ms.value, "ms", n / ms.value / 1e3, "Mpts/s", flush=True)
+        # plain per-window buckets, then the window-table mode the prover uses (tables built once, untimed)
+        for mode, tag in ((0, "plain"), (1, "tables")):
+            lib.fb_set_msm_tables(mode)
+            fb.native.check(lib.fb_test_msm(ctx.handle, group, bases.ctypes.data, a.ctypes.data, n, res.ctypes.data, 3, C.byref(ms)))
+            out[f"msm_g{group}_{tag}_ms_2^{lg}"] = ms.value
+            out[f"msm_g{group}_{tag}_mpts_2^{lg}"] = n / ms.value / 1e3
+            print(lg, "msm g", group, tag, ms.value, "ms", n / ms.value / 1e3, "Mpts/s", flush=True)
+        lib.fb_set_msm_tables(-1)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/probe.json", "w"), indent=1)
 print(json.dumps(out))
