@@ -209,6 +209,10 @@ def run_ours(args):
             os.close(saved)
     torch.cuda.set_device(local)
     ctx = fb.Context(local)
+    if os.environ.get("FB_MSM_BA") is not None:      # experiment switches (defaults: tables auto, batch-affine on)
+        fb.native.lib.fb_set_msm_batch_affine(int(os.environ["FB_MSM_BA"]))
+    if os.environ.get("FB_MSM_TABLES") is not None:
+        fb.native.lib.fb_set_msm_tables(int(os.environ["FB_MSM_TABLES"]))
     if world > 1:
         # the library's own NCCL communicator (four-step NTT exchange): id from rank 0 to everybody
         import torch.distributed as dist

@@ -277,6 +277,8 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   const MsmPlan msm_plans[4] = {pk->plan_h, pk->plan_l, pk->plan_a, pk->plan_b};
   int arc = 0;
   for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_plans[i], 1, i == 3);
+  if (!arc && g_msm_batch_affine)  // optional buffers: a scratch that cannot get them accumulates in XYZZ only
+    for (int i = 0; i < 4; i++) pk->msm[i].alloc_batch_affine(&msm_plans[i], 1, i == 3);
   if (arc != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
@@ -418,6 +420,7 @@ static void* build_host_tables(const ProvingKey* pk) {
 }
 
 int g_msm_tables = -1;
+int g_msm_batch_affine = 0;
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
 
 // Result slots: five arrays of MSM_VBITS bit sums (G2-sized slots), order H L A B1 B2.
@@ -828,6 +831,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
 uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
+void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 2) ? 0 : on; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {

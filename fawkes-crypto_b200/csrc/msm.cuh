@@ -32,6 +32,7 @@ constexpr int MSM_MIN_TASK_LOG = 4;
 constexpr uint32_t MSM_MIN_TASK = 1u << MSM_MIN_TASK_LOG;
 constexpr uint32_t MSM_HEAVY = 32;        // partials per bucket handled by one thread
 constexpr int MSM_HEAVY_THREADS = 128;
+constexpr int MSM_BA_MAX_ROUNDS = 6;
 constexpr int MSM_VBITS = 288;            // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
 
 struct MsmPlan {
@@ -52,6 +53,15 @@ struct MsmPlan {
   uint32_t nsegs() const { return nbuckets() >> seg_log; }
   int vbits() const { return wred() * c; }                     // V entries the host Horner consumes
   uint64_t table_points() const { return table ? (uint64_t)n * W : n; }
+  // batch-affine rounds before the XYZZ accumulation: halve the entries per bucket until ~12 are left
+  bool ba_force = false;  // tests: run the rounds on small inputs too (fb_set_msm_batch_affine(2))
+  int ba_rounds() const {
+    const uint64_t N = (uint64_t)n * W;
+    if (!ba_force && N < (1u << 16)) return 0;
+    int r = 0;
+    while (r < MSM_BA_MAX_ROUNDS && (N >> (r + 1)) >= (ba_force ? 1ull : 12ull) * nbuckets()) r++;
+    return r;
+  }
 };
 
 // Scratch shared by consecutive MSMs on one stream (sized for the largest plan).
@@ -69,8 +79,16 @@ struct MsmScratch {
   uint32_t* task_off = nullptr; // [nbuckets + 1]
   void* partials = nullptr;     // [cap_tasks] XYZZ
   uint32_t* heavy = nullptr;    // [0] = count, then bucket ids
+  // batch-affine pre-reduction (msm.cu, "batch-affine rounds"); all null when the scratch was allocated without
+  uint32_t* ba_off = nullptr;   // [MSM_BA_MAX_ROUNDS][nbuckets + 1] bucket offsets of every level
+  uint32_t* ba_cnt = nullptr;   // [nbuckets + 1]
+  uint32_t* ba_src = nullptr;   // per level: first input slot of every output slot (| pair flag)
+  void* ba_pr = nullptr;        // prefix products of the round in flight (one field element per output slot)
+  void* ba_pts[2] = {nullptr, nullptr};  // affine points of the odd / even levels
+  uint64_t ba_cap = 0;          // entries the batch-affine buffers were sized for (0 = disabled)
   size_t cap_entries = 0, cap_buckets = 0, cap_tasks = 0;
   int alloc(const MsmPlan* plans, int count, bool need_g2);
+  int alloc_batch_affine(const MsmPlan* plans, int count, bool need_g2);  // optional, after alloc()
   void release();
 };
 

@@ -312,6 +312,7 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   }
   MsmScratch scr;
   if (scr.alloc(&plan, 1, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
+  if (g_msm_batch_affine) scr.alloc_batch_affine(&plan, 1, group == 2);
   std::vector<G2XYZZ> hres(MSM_VBITS);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);

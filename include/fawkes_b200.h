@@ -165,6 +165,11 @@ void fb_set_serial(int on);
  * -1 auto (default: on when they fit in free HBM with headroom), 0 off, 1 on.  Applies to keys loaded
  * afterwards and to fb_test_msm. */
 void fb_set_msm_tables(int mode);
+/* Batch-affine pre-reduction of the sorted bucket entries (pairwise affine adds sharing one inversion per
+ * warp) in front of the XYZZ accumulation: 0 off (default -- exact, but measured slower than the XYZZ
+ * kernel on B200), 1 on, 2 on even for small inputs (tests).  Applies to keys loaded
+ * afterwards and to fb_test_msm. */
+void fb_set_msm_batch_affine(int on);
 void fb_kernel_stats_enable(int on);
 void fb_kernel_stats_reset(void);
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms);
