@@ -384,6 +384,9 @@ def run_ours(args):
                    "parallelism": (f"MSM bases sharded by index x{world}; R1CS rows + four-step NTT sharded x{world} "
                                    "(NCCL all-to-all) when world is a power of two, else replicated")
                    if world > 1 else "single GPU",
+                   "msm": {"window_bits": info["msm_window_bits"], "digits_per_scalar": info["msm_windows"],
+                           "window_tables": bool(info["msm_tables"]), "table_bytes": info["table_bytes"],
+                           "batch_affine_rounds": bool(info["msm_batch_affine"])},
                    "l2": "256 MiB buffer written between timed iterations; working set also exceeds L2",
                    "schedule": "L/A/B MSMs on side streams beside R1CS eval + H pipeline + H MSM; kernel_ms and "
                                "roofline come from a serial-schedule pass of the same workload",

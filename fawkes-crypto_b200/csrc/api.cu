@@ -742,6 +742,10 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
                          (uint64_t)pk->plan_a.n * pk->plan_a.W + (uint64_t)pk->plan_b.n * pk->plan_b.W;
   info->g2_digit_slots = (uint64_t)pk->plan_b.n * pk->plan_b.W;
   info->msm_window_bits = pk->plan_h.c;
+  info->msm_windows = pk->plan_h.W;
+  info->msm_tables = pk->plan_h.table ? 1 : 0;
+  info->msm_batch_affine = pk->msm[0].ba_cap ? 1 : 0;
+  info->table_bytes = pk->table_bytes;
   return FB_OK;
 }
 

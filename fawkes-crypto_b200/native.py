@@ -30,7 +30,8 @@ class PkInfo(C.Structure):
                 ("log_m", C.c_uint32), ("len_h", C.c_uint32), ("len_l", C.c_uint32),
                 ("len_a", C.c_uint32), ("len_b", C.c_uint32), ("nnz", C.c_uint64),
                 ("hbm_bytes", C.c_uint64), ("g1_digit_slots", C.c_uint64), ("g2_digit_slots", C.c_uint64),
-                ("msm_window_bits", C.c_uint32)]
+                ("msm_window_bits", C.c_uint32), ("msm_windows", C.c_uint32), ("msm_tables", C.c_uint32),
+                ("msm_batch_affine", C.c_uint32), ("table_bytes", C.c_uint64)]
 
 
 # every symbol declared in include/fawkes_b200.h: (restype, argtypes)

@@ -70,6 +70,10 @@ typedef struct fb_pk_info {
   uint64_t g1_digit_slots; /* sum over the four G1 MSMs of n x windows = mixed adds per prove (upper bound) */
   uint64_t g2_digit_slots;
   uint32_t msm_window_bits; /* window size chosen for the H MSM */
+  uint32_t msm_windows;     /* digits per scalar of the H MSM */
+  uint32_t msm_tables;      /* 1 if the key holds the 2^(c w) P window tables */
+  uint32_t msm_batch_affine; /* 1 if the batch-affine rounds are enabled for this key */
+  uint64_t table_bytes;     /* part of hbm_bytes held by the window tables */
 } fb_pk_info;
 
 /* ---- context --------------------------------------------------------------- */

@@ -235,3 +235,42 @@ def test_prove_2_20_bytes_equal_cpp_oracle(ctx):
     cproof, _ = bench.cpu_prove_once(fb, circ, params, tdi, cpu.hw_threads())
     assert proof.to_raw() == cproof
     params.unload()
+
+
+def test_cfg1_poseidon_merkle_setup_prove_verify(ctx):
+    """configs[0]: the reference's own hot-path test (tests/bellman_groth16.rs:19-47) -- Poseidon Merkle
+    proof of depth 32, 7,328 + 34 gates, rows with up to ~55 terms -- built by the front-end restatement
+    (oracle/frontend.py), then setup + prove + verify through the C ABI with a fixed trapdoor and r, s.
+    The proof must equal the C++ CPU restatement's byte for byte, go through the reference's byte framing
+    (Parameters::write/read, brotli gate blob) unchanged, and verify; a wrong root must not."""
+    import random
+    import fawkes_crypto_b200 as fb
+    import bench
+    from oracle import cpu
+    from oracle import frontend as fe
+    rng = random.Random(2026)
+    leaf = rng.randrange(bn.R)
+    sibling = [rng.randrange(bn.R) for _ in range(32)]
+    path = [rng.random() < 0.5 for _ in range(32)]
+    gates, inp, aux = fe.merkle_circuit(leaf, sibling, path)
+    assert len(gates) == 7362 and len(aux) == 7394
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    circ = fb.Circuit.from_raw_gates(raw, len(gates), 2, len(aux))
+    assert circ.shape()["n_gates"] == 7362
+    td, r, s = synth.synth_trapdoor(synth.SEED_BASE + 1)
+    tdi = [td.alpha, td.beta, td.gamma, td.delta, td.tau]
+    params = fb.setup(circ, ctx, trapdoor=tdi, gates_blob=codec.brotli_compress(raw))
+    params = fb.Parameters.read(params.write())            # reference framing, gate blob included
+    wi, wa = fr_np(inp), fr_np(aux)
+    inputs, proof = fb.groth16.prove_with_rs(params, wi, wa, r, s, ctx)
+    assert params.info()["log_m"] == 13 and params.info()["n_gates"] == 7362
+    assert fr_list(inputs) == inp[1:]
+    assert fb.verify(params.get_vk(), proof, inputs)
+    assert not fb.verify(params.get_vk(), proof, fr_np([(inp[1] + 1) % bn.R]))
+    # byte parity with the CPU restatement on the same key and witness
+    sh = circ.shape()
+    rp, cl, cf = bench.expand_csr(fb, circ)
+    ref, _, _ = cpu.prove(params.bellman_bytes, sh["n_gates"], sh["n_in"], sh["n_aux"], rp, cl, cf, wi, wa,
+                          fb.groth16.fr_raw(r), fb.groth16.fr_raw(s), 4)
+    assert proof.to_raw() == ref
+    params.unload()
