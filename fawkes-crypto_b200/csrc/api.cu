@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cstring>
 #include <future>
+#include <thread>
 
 #include "internal.h"
 
@@ -59,10 +60,14 @@ static void free_host_tables(void* p);
 static void* build_host_tables(const ProvingKey* pk);
 static void pk_release(ProvingKey* pk) {
   if (!pk) return;
-  cudaFree(pk->h); cudaFree(pk->l); cudaFree(pk->a); cudaFree(pk->b1); cudaFree(pk->b2);
-  cudaFree(pk->a_map); cudaFree(pk->b_map);
-  free_csr(pk->csr);
-  pk->dom.destroy();
+  for (ProvingKey* s : pk->slots) pk_release(s);
+  pk->slots.clear();
+  if (!pk->is_slot) {  // a slot only borrows the immutable arrays
+    cudaFree(pk->h); cudaFree(pk->l); cudaFree(pk->a); cudaFree(pk->b1); cudaFree(pk->b2);
+    cudaFree(pk->a_map); cudaFree(pk->b_map);
+    free_csr(pk->csr);
+    pk->dom.destroy();
+  }
   cudaFree(pk->w);
   for (int i = 0; i < 3; i++) { cudaFree(pk->ev[i]); cudaFree(pk->xtmp[i]); }
   cudaFree(pk->scratch);
@@ -70,7 +75,16 @@ static void pk_release(ProvingKey* pk) {
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
   for (auto& e : pk->msm_done) if (e) cudaEventDestroy(e);
-  if (pk->host_tables) free_host_tables(pk->host_tables);
+  if (pk->is_slot) {
+    Ctx* c = pk->ctx;
+    if (c) {
+      cudaStreamDestroy(c->stream);
+      for (int i = 0; i < 3; i++) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
+      delete c;
+    }
+  } else if (pk->host_tables) {
+    free_host_tables(pk->host_tables);
+  }
   delete pk;
 }
 
@@ -78,8 +92,11 @@ struct Timing {
   cudaEvent_t ev[6];
   float ms[6] = {0, 0, 0, 0, 0, 0};
   bool init = false;
+  ~Timing() {  // thread_local: the batch worker threads release their events on exit
+    if (init) for (auto& e : ev) cudaEventDestroy(e);
+  }
 };
-static Timing g_timing;  // one key in flight per process
+static thread_local Timing g_timing;  // per calling thread (fb_prove_batch proves on several)
 
 static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
                     int shard, int nshards, ProvingKey** out) {
@@ -759,17 +776,88 @@ int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, cons
                     proof_raw, nullptr, h_out);
 }
 
-int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
+// A slot = everything one prove writes (witness, evaluations, MSM scratch, result buffers, events) plus its
+// own streams, next to a borrowed view of the key's immutable arrays.
+static ProvingKey* make_slot(const ProvingKey* pk) {
+  ProvingKey* s = new ProvingKey(*pk);
+  s->is_slot = true;
+  s->slots.clear();
+  s->w = nullptr; s->scratch = nullptr; s->results = nullptr; s->results_host = nullptr;
+  for (auto& p : s->ev) p = nullptr;
+  for (auto& p : s->xtmp) p = nullptr;
+  for (auto& m : s->msm) m = MsmScratch();
+  for (auto& e : s->msm_done) e = nullptr;
+  Ctx* c = new Ctx();
+  c->device = pk->ctx->device;
+  s->ctx = c;
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; i++)
+    ok = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->aux_done[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->w, ((size_t)(pk->n_in + pk->n_aux) + 1) * sizeof(Fr)) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; i++) ok = cudaMalloc(&s->ev[i], pk->m * sizeof(Fr)) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->scratch, pk->m * sizeof(Fr)) == cudaSuccess;
+  const MsmPlan plans[4] = {pk->plan_h, pk->plan_l, pk->plan_a, pk->plan_b};
+  for (int i = 0; i < 4 && ok; i++) ok = s->msm[i].alloc(&plans[i], 1, i == 3) == 0;
+  ok = ok && cudaMalloc(&s->results, 5 * MSM_VBITS * sizeof(G2XYZZ)) == cudaSuccess;
+  for (auto& e : s->msm_done) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaMallocHost(&s->results_host, 5 * MSM_VBITS * sizeof(G2XYZZ)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    pk_release(s);
+    return nullptr;
+  }
+  return s;
+}
+
+int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
                    const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
                    uint8_t* proofs_raw) {
   if (!inputs || (!aux && n_aux) || !r || !s || !proofs_raw) { set_error("fb_prove_batch: null buffer"); return FB_ERR_ARG; }
   // The reference proves one circuit per prove() call (prover.rs:63-90); a batch is the same key used
-  // `count` times.  Proofs are independent, so they are simply issued back to back on the resident key.
-  for (uint32_t i = 0; i < count; i++) {
-    int rc = fb_prove(ctx, pk, inputs[i], n_in, aux ? aux[i] : nullptr, n_aux, r + 4 * (size_t)i, s + 4 * (size_t)i,
-                      proofs_raw + 256 * (size_t)i, nullptr);
-    if (rc) return rc;
+  // `count` times.  The proofs are independent and a small prove is a chain of ~70 tiny launches that
+  // leaves the GPU idle, so up to FB_BATCH_SLOTS (default 8) of them are kept in flight: one host thread
+  // and one set of streams and workspaces per slot, all reading the same resident key.
+  ProvingKey* pk = reinterpret_cast<ProvingKey*>(pk_);
+  Ctx* c0 = reinterpret_cast<Ctx*>(ctx);
+  if (!pk || !c0) { set_error("fb_prove_batch: null handle"); return FB_ERR_ARG; }
+  int want = 8;
+  if (const char* e = getenv("FB_BATCH_SLOTS")) want = std::max(1, std::min(32, atoi(e)));
+  // big keys saturate the GPU on their own (and their workspaces are large); sharded keys prove collectively
+  if (pk->m > (1u << 16) || pk->nshards != 1 || pk->dist_g || g_serial) want = 1;
+  want = (int)std::min<uint32_t>((uint32_t)want, count);
+  FB_CUDA(cudaSetDevice(c0->device));
+  while ((int)pk->slots.size() + 1 < want) {
+    ProvingKey* sl = make_slot(pk);
+    if (!sl) break;  // out of memory: run with the slots we have
+    pk->slots.push_back(sl);
   }
+  const int K = std::min<int>(want, (int)pk->slots.size() + 1);
+  if (K <= 1) {
+    for (uint32_t i = 0; i < count; i++) {
+      int rc = fb_prove(ctx, pk_, inputs[i], n_in, aux ? aux[i] : nullptr, n_aux, r + 4 * (size_t)i, s + 4 * (size_t)i,
+                        proofs_raw + 256 * (size_t)i, nullptr);
+      if (rc) return rc;
+    }
+    return FB_OK;
+  }
+  std::vector<int> rcs(K, FB_OK);
+  std::vector<std::string> errs(K);
+  std::vector<std::thread> th;
+  for (int t = 0; t < K; t++) {
+    th.emplace_back([&, t]() {
+      ProvingKey* p = t == 0 ? pk : pk->slots[t - 1];
+      Ctx* c = t == 0 ? c0 : p->ctx;
+      for (uint32_t i = t; i < count; i += K) {
+        int rc = prove_impl(c, p, inputs[i], n_in, aux ? aux[i] : nullptr, n_aux, nullptr, r + 4 * (size_t)i,
+                            s + 4 * (size_t)i, proofs_raw + 256 * (size_t)i, nullptr, nullptr);
+        if (rc) { rcs[t] = rc; errs[t] = last_error_cstr(); return; }
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  for (int t = 0; t < K; t++)
+    if (rcs[t]) { set_error("%s", errs[t].c_str()); return rcs[t]; }
   return FB_OK;
 }
 

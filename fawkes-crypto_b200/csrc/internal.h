@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -24,8 +25,8 @@ extern int g_msm_tables;
 extern int g_msm_batch_affine;
 
 // ---- instrumentation (bench.py: gpu_launches and the live roofline timing) -------------
-extern unsigned long long g_launches;           // kernels launched by this library
-inline void count_launch(int n = 1) { g_launches += n; }
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 enum { KSTAT_ACC_G1 = 0, KSTAT_ACC_G2 = 1, KSTAT_NTT = 2, KSTAT_KINDS = 3 };
 void kstat_begin(int kind, cudaStream_t st);    // no-ops unless enabled
 void kstat_end(int kind, cudaStream_t st);
@@ -103,6 +104,10 @@ struct ProvingKey {
   Fr* xtmp[3] = {nullptr, nullptr, nullptr};
   void* host_tables = nullptr;  // fixed-base tables of delta/alpha/beta for the host-side assembly
   uint64_t table_bytes = 0;     // HBM held by the MSM window tables beyond the plain base arrays
+  // fb_prove_batch: extra per-prove workspaces ("slots") that share this key's immutable arrays (bases and
+  // window tables, CSR, twiddles, host tables) and own everything a prove writes, each with its own streams
+  bool is_slot = false;
+  std::vector<ProvingKey*> slots;
 };
 
 struct Circuit {

@@ -29,7 +29,7 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error_cstr() { return g_err.c_str(); }
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 namespace {
 struct KStat {
   bool enabled = false;
