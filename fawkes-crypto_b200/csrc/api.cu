@@ -98,8 +98,8 @@ struct Timing {
 };
 static thread_local Timing g_timing;  // per calling thread (fb_prove_batch proves on several)
 
-static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
-                    int shard, int nshards, ProvingKey** out) {
+static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
+                         int shard, int nshards, bool allow_tables, bool* used_tables, ProvingKey** out) {
   if (!ctx || !params || !circ || !out || nshards < 1 || shard < 0 || shard >= nshards) {
     set_error("fb_pk_load: bad argument");
     return FB_ERR_ARG;
@@ -190,7 +190,7 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
     slice(v.n_a, lo, cnt_a);
     slice(v.n_b1, lo, cnt_b);
     bool tables = g_msm_tables == 1;
-    if (g_msm_tables < 0) {
+    if (g_msm_tables < 0 && allow_tables) {
       const MsmPlan th = MsmPlan::make((uint32_t)cnt_h, true), tl = MsmPlan::make((uint32_t)cnt_l, true),
                     ta = MsmPlan::make((uint32_t)cnt_a, true), tb = MsmPlan::make((uint32_t)cnt_b, true);
       const uint64_t need = (th.table_points() + tl.table_points() + ta.table_points()) * 64 + tb.table_points() * 192;
@@ -199,6 +199,7 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
       // everything else a key holds (CSR, twiddles, workspaces, MSM scratch) is ~25 x 32 B per row
       tables = need + (uint64_t)m * 32 * 25 + (8ull << 30) < free_b;
     }
+    *used_tables = tables;
     pk->plan_h = MsmPlan::make((uint32_t)cnt_h, tables);
     pk->plan_l = MsmPlan::make((uint32_t)cnt_l, tables);
     pk->plan_a = MsmPlan::make((uint32_t)cnt_a, tables);
@@ -310,6 +311,19 @@ static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* 
   return FB_OK;
 #undef PK_TRY
 #undef PK_CUDA
+}
+
+// In auto mode the window tables are a best-effort use of free HBM: if the estimate was too optimistic and
+// an allocation fails, the key is loaded again with plain 64-byte bases instead of failing the load.
+static int load_key(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
+                    int shard, int nshards, ProvingKey** out) {
+  bool used_tables = false;
+  int rc = load_key_once(ctx, params, len, circ, checked, shard, nshards, true, &used_tables, out);
+  if (rc == FB_ERR_CUDA && used_tables && g_msm_tables < 0) {
+    cudaGetLastError();
+    rc = load_key_once(ctx, params, len, circ, checked, shard, nshards, false, &used_tables, out);
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------- assembly ---

@@ -17,6 +17,14 @@ __device__ inline Fq fq2_probe(const Fq& x, const Fq& y) {
   Fq2 m = mul(Fq2{x, y}, Fq2{y, mul_c(x, x)});
   return sub(m.c0, m.c1);
 }
+// msub2 over Fq2 (two shared reductions) against four separate products: returns 0 when they agree
+__device__ inline Fq fq2_probe2(const Fq& x, const Fq& y) {
+  const Fq2 a{x, y}, b{y, mul_c(x, x)}, c{mul_c(y, y), x}, d{add(x, y), sub(x, y)};
+  const Fq2 want = sub(mul(a, b), mul(c, d)), got = msub2(a, b, c, d);
+  const Fq2 e = sub(want, got);
+  return add(add(e.c0, e.c1), add(e.c0, e.c0));   // 0 iff e == 0 up to a negligible cancellation
+}
+__device__ inline Fr fq2_probe2(const Fr& x, const Fr&) { return Fr::zero(); }
 __device__ inline Fr fq2_probe(const Fr& x, const Fr&) { return x; }
 
 template <class C>
@@ -32,6 +40,7 @@ __global__ void k_field_op(int op, const Fp<C>* a, const Fp<C>* b, Fp<C>* out, u
       case 5: r = sqr(x); break;                         // dedicated square (36 + 72 wide MACs)
       case 6: r = msub2(x, y, y, sqr(x)); break;         // x*y - y*x^2, one shared reduction
       case 7: r = fq2_probe(x, y); break;                // Fq only: lazy-reduction Fq2 product
+      case 8: r = fq2_probe2(x, y); break;               // Fq only: Fq2 a*b - c*d with shared reductions (-> 0)
       default: r = mul_c(x, y); break;
     }
     out[i] = r;

@@ -42,6 +42,8 @@ def test_field_ops_match_integers(ctx, field):
     if field == 1:  # Fq2 product with lazy reduction: (x + y u)(y + x^2 u), u^2 = -1, reported as c0 - c1
         want = [((x * y - y * x * x) - (x * x * x + y * y)) % mod for x, y in zip(av, bv)]
         assert to_list(run_op(ctx, field, 7, a, b)) == want
+        # Fq2 a*b - c*d with two shared reductions equals the four-product form (difference is zero)
+        assert not np.any(run_op(ctx, field, 8, a, b))
 
 
 @pytest.mark.parametrize("field", [0, 1])
