@@ -246,6 +246,10 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
 }
 
 // ------------------------------------------------------------ accumulate ---
+#ifndef FB_G2_ACC_CTAS
+#define FB_G2_ACC_CTAS 2
+#endif
+#define MSM_ACC_MIN_CTAS(F) (sizeof(F) == sizeof(Fq) ? 4 : FB_G2_ACC_CTAS)
 // Equal-length tasks: thread t accumulates the sorted entries [t*T, (t+1)*T), T = 2^task_log, and
 // flushes a partial sum whenever the bucket changes.  Every thread performs exactly T mixed adds
 // (no divergence in trip count, no matter how skewed the digits are: a bucket holding a third of
@@ -254,7 +258,7 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
 // floor((end_b - 1) / T), so no second scan is needed to find them.
 // DIRECT: `bases` already holds the points in sorted order (output of the batch-affine rounds).
 template <class F, bool DIRECT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MSM_ACC_MIN_CTAS(F))
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
              XYZZ<F>* __restrict__ partials) {
