@@ -8,9 +8,12 @@
 
 namespace fb {
 
-constexpr int NTT_LOG_TILE = 12;   // 4096 elements = 128 KiB of shared memory per CTA
+// 1024 elements = 32 KiB of shared memory per CTA, 256 threads: five CTAs per SM overlap each other's load,
+// compute and store phases.  Measured H pipeline at 2^24: 35.7 ms with 128 KiB tiles x 512 threads (one CTA
+// per SM), 30.0 with 64 KiB x 512, 28.4 with 64 KiB x 256, 27.3 with 32 KiB x 256, 28.6 with 16 KiB x 256.
+constexpr int NTT_LOG_TILE = 10;
 constexpr int NTT_MIN_LO = 3;      // strided passes move >= 8 consecutive elements (256 B)
-constexpr int NTT_THREADS = 512;
+constexpr int NTT_THREADS = 256;
 
 // Transport of the distributed transform: every rank sends chunk r (count elements) of each of
 // `narrays` send buffers to rank r and receives chunk r of each recv buffer from rank r.
