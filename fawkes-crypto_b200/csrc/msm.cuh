@@ -7,16 +7,16 @@
 // bellman's (c = ln n unsigned windows, Jacobian) gives byte-identical affine output.
 //
 // Pipeline (all on one stream):
-//   1. k_digits_count  canonical scalar (one Montgomery multiply by 1) -> signed
-//                      base-2^c digits d in [-2^(c-1), 2^(c-1)], histogram of
-//                      bucket = window * 2^(c-1) + |d| - 1
+//   0. (key load)      window tables: 2^(c w) P_i for every window w next to the bases (k_build_window_table),
+//                      so that all windows share ONE set of 2^(c-1) buckets and c can grow by ~4 bits
+//   1. k_digits<0>     canonical scalar (one Montgomery multiply by 1) -> signed base-2^c digits d in
+//                      [-2^(c-1), 2^(c-1)], histogram of bucket = |d| - 1 (+ window * 2^(c-1) without tables)
 //   2. k_scan_*        exclusive prefix sum of the histogram (bucket offsets)
-//   3. k_scatter       counting-sort placement of (point index | sign << 31)
-//   4. k_accumulate    bucket runs cut into tasks of <= 2^task_log entries (a scan of the
-//                      per-bucket task counts maps task -> bucket); one thread per task,
-//                      XYZZ mixed adds, next base prefetched while the current add runs;
-//                      k_bucket_gather / k_bucket_heavy fold task partials into buckets
-//   5. k_bucket_segments / k_segment_bits   per-segment short running sums, then the segment
+//   3. k_digits<1>     counting-sort placement of (w * n + i | sign << 31)
+//   4. k_accumulate    equal-length tasks of 2^task_log sorted entries per thread, XYZZ mixed adds, a partial
+//                      flushed at every bucket change; k_bucket_gather / k_bucket_heavy fold the partials
+//      (optional: k_ba_* batch-affine rounds in front of it, off by default -- see msm.cu)
+//   5. k_bucket_segments / k_segment_bits / k_fold_parts   per-segment short running sums, then the segment
 //                      sums combined bit-wise into V[p] (weight 2^p)
 //   6. (host)          sum_p 2^p V[p] by Horner on a CPU core: msm_horner_host
 // Bases are resident in HBM in Montgomery affine form, 64 B (G1) / 128 B (G2).
