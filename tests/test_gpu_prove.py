@@ -274,3 +274,24 @@ def test_cfg1_poseidon_merkle_setup_prove_verify(ctx):
                           fb.groth16.fr_raw(r), fb.groth16.fr_raw(s), 4)
     assert proof.to_raw() == ref
     params.unload()
+
+
+def test_prove_2_24_full_size_verifies(ctx):
+    """BASELINE configs[3] at full size (2^24 rows, 75 GB resident key with window tables): the proof passes
+    the pairing check (a size-independent end-to-end property: A, B and C are right only if all five
+    MSMs over 16.7 M points and the seven 2^24-point transforms are), the public input is echoed, a
+    tampered input fails, and proving twice gives the same bytes."""
+    import fawkes_crypto_b200 as fb
+    import bench
+    circ, params, tdi, _ = bench.make_case(fb, ctx, 24)
+    wi, wa = circ.witness()
+    inputs, proof = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
+    assert params.info()["log_m"] == 24 and params.info()["msm_tables"] == 1
+    assert np.array_equal(np.asarray(inputs), wi[1:])
+    assert fb.verify(params.get_vk(), proof, inputs)
+    bad = np.array(wi[1:], copy=True)
+    bad[0, 0] ^= np.uint64(1)
+    assert not fb.verify(params.get_vk(), proof, bad)
+    _, proof2 = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
+    assert proof2.to_raw() == proof.to_raw()
+    params.unload()
