@@ -75,6 +75,8 @@ static void pk_release(ProvingKey* pk) {
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
   for (auto& e : pk->msm_done) if (e) cudaEventDestroy(e);
+  if (pk->graph_exec) cudaGraphExecDestroy(pk->graph_exec);
+  if (pk->w_stage) cudaFreeHost(pk->w_stage);
   if (pk->is_slot) {
     Ctx* c = pk->ctx;
     if (c) {
@@ -453,6 +455,8 @@ static void* build_host_tables(const ProvingKey* pk) {
 int g_msm_tables = -1;
 int g_msm_batch_affine = 0;
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
+static int g_prove_graph = -1; // CUDA-graph replay for small keys: -1 = on unless FB_PROVE_GRAPH=0, 0 off, 1 on
+bool kstat_enabled();
 
 // Result slots: five arrays of MSM_VBITS bit sums (G2-sized slots), order H L A B1 B2.
 static inline G2XYZZ* vslot(void* base, int i) { return reinterpret_cast<G2XYZZ*>(base) + (size_t)i * MSM_VBITS; }
@@ -531,6 +535,68 @@ static void collect_timings(double host_ms, double total_ms) {
   T.ms[5] = (float)total_ms;
 }
 
+// Small keys (domain <= 2^16): a prove is ~70 launches of tiny kernels on four streams and is bound by
+// launch latency, not by the GPU.  The device side is captured once per key (per batch slot) as a CUDA
+// graph -- witness upload from a pinned staging buffer, the witness-only MSMs forked onto their streams,
+// R1CS + H pipeline + H MSM, the five result copies, joined back -- and replayed with one launch per
+// proof; the host tails then run on the calling thread (a few microseconds each at these window sizes).
+static int prove_graph(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
+                       uint32_t n_aux, const uint64_t* r, const uint64_t* s, uint8_t* proof_raw, bool* fell_back) {
+  *fell_back = false;
+  auto t0 = std::chrono::steady_clock::now();
+  FB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t wbytes = (size_t)(n_in + n_aux) * sizeof(Fr);
+  if (!pk->w_stage) FB_CUDA(cudaMallocHost(&pk->w_stage, std::max<size_t>(wbytes, 32)));
+  if (!pk->graph_exec) {
+    const unsigned long long l0 = g_launches.load();
+    bool ok = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    int rc = FB_OK;
+    if (ok) {
+      ok = cudaMemcpyAsync(pk->w, pk->w_stage, wbytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
+      if (ok) rc = prove_launch(pk, nullptr);
+      for (int e = 3; e >= 1 && ok && !rc; e--) ok = cudaStreamWaitEvent(st, pk->msm_done[e], 0) == cudaSuccess;
+      cudaGraph_t g = nullptr;
+      const cudaError_t ee = cudaStreamEndCapture(st, &g);
+      ok = ok && !rc && ee == cudaSuccess && g;
+      if (ok) ok = cudaGraphInstantiate(&pk->graph_exec, g, 0) == cudaSuccess;
+      if (g) cudaGraphDestroy(g);
+    }
+    pk->graph_launches = g_launches.load() - l0;
+    g_launches.store(l0);  // captured, not run
+    if (!ok) {
+      cudaGetLastError();
+      pk->graph_exec = nullptr;
+      pk->graph_failed = true;
+      *fell_back = true;
+      return FB_OK;
+    }
+  }
+  memcpy(pk->w_stage, inputs, (size_t)n_in * sizeof(Fr));
+  if (n_aux) memcpy((uint8_t*)pk->w_stage + (size_t)n_in * sizeof(Fr), aux, (size_t)n_aux * sizeof(Fr));
+  FB_CUDA(cudaGraphLaunch(pk->graph_exec, st));
+  count_launch((int)pk->graph_launches);
+  FixedTerms ft;
+  VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
+  const int rc_fixed = fixed_terms(&vk, reinterpret_cast<const KeyTables*>(pk->host_tables), r, s, ft);
+  FB_CUDA(cudaStreamSynchronize(st));
+  FB_CUDA(cudaGetLastError());
+  if (rc_fixed) return rc_fixed;
+  auto t1 = std::chrono::steady_clock::now();
+  const H2 B2 = msm_horner_host<HFq2>(vslot(pk->results_host, 4), pk->plan_b.vbits());
+  const H1 B1 = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 3), pk->plan_b.vbits());
+  const H1 A = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 2), pk->plan_a.vbits());
+  const H1 L = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 1), pk->plan_l.vbits());
+  const H1 H = msm_horner_host<HFq>((const G1XYZZ*)vslot(pk->results_host, 0), pk->plan_h.vbits());
+  finish_proof(ft, H, L, A, B1, B2, nullptr, nullptr, proof_raw);
+  auto t2 = std::chrono::steady_clock::now();
+  Timing& T = g_timing;  // stage events cannot be read out of a graph: only host and total are reported
+  T.ms[0] = T.ms[1] = T.ms[2] = T.ms[3] = 0;
+  T.ms[4] = (float)std::chrono::duration<double, std::milli>(t2 - t1).count();
+  T.ms[5] = (float)std::chrono::duration<double, std::milli>(t2 - t0).count();
+  return FB_OK;
+}
+
 static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t n_in,
                       const uint64_t* aux, uint32_t n_aux, const void* dev_w, const uint64_t* r,
                       const uint64_t* s, uint8_t* proof_raw, uint8_t* partial, uint64_t* h_out) {
@@ -538,6 +604,20 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
   if (!dev_w && (n_in != pk->n_in || n_aux != pk->n_aux)) {
     set_error("witness has n_in=%u n_aux=%u, key expects %u / %u", n_in, n_aux, pk->n_in, pk->n_aux);
     return FB_ERR_ARG;
+  }
+  if (g_prove_graph < 0) {
+    const char* e = getenv("FB_PROVE_GRAPH");
+    g_prove_graph = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (g_prove_graph && !dev_w && !partial && !h_out && !g_serial && !kstat_enabled() && pk->nshards == 1 &&
+      !pk->dist_g && pk->m <= (1ull << 16) && !pk->graph_failed) {
+    if (!g_timing.init) {
+      for (auto& e : g_timing.ev) cudaEventCreate(&e);
+      g_timing.init = true;
+    }
+    bool fell_back = false;
+    const int grc = prove_graph(ctx, pk, inputs, n_in, aux, n_aux, r, s, proof_raw, &fell_back);
+    if (!fell_back) return grc;
   }
   auto t0 = std::chrono::steady_clock::now();
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -796,6 +876,7 @@ static ProvingKey* make_slot(const ProvingKey* pk) {
   ProvingKey* s = new ProvingKey(*pk);
   s->is_slot = true;
   s->slots.clear();
+  s->graph_exec = nullptr; s->w_stage = nullptr; s->graph_launches = 0; s->graph_failed = false;
   s->w = nullptr; s->scratch = nullptr; s->results = nullptr; s->results_host = nullptr;
   for (auto& p : s->ev) p = nullptr;
   for (auto& p : s->xtmp) p = nullptr;
@@ -937,6 +1018,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
 uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
+void fb_set_prove_graph(int on) { fb::g_prove_graph = on ? 1 : 0; }
 void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 2) ? 0 : on; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }

@@ -108,6 +108,12 @@ struct ProvingKey {
   // window tables, CSR, twiddles, host tables) and own everything a prove writes, each with its own streams
   bool is_slot = false;
   std::vector<ProvingKey*> slots;
+  // small keys: the whole device side of a prove (upload, ~70 kernels on four streams, result copies)
+  // captured once as a CUDA graph and replayed per proof (api.cu: prove_graph)
+  cudaGraphExec_t graph_exec = nullptr;
+  void* w_stage = nullptr;               // pinned staging copy of the witness (fixed address for the graph)
+  unsigned long long graph_launches = 0; // kernels inside the graph (for fb_launch_count)
+  bool graph_failed = false;             // capture was refused once: stay on the stream path
 };
 
 struct Circuit {

@@ -64,6 +64,7 @@ void kstat_end(int kind, cudaStream_t st) {
   }
 }
 void kstat_enable(bool on) { g_ks.enabled = on; }
+bool kstat_enabled() { return g_ks.enabled; }
 void kstat_reset() {
   for (auto& r : g_ks.recs) { g_ks.pool.push_back(r.a); g_ks.pool.push_back(r.b); }
   g_ks.recs.clear();

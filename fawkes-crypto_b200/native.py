@@ -66,6 +66,7 @@ SIGNATURES = {
     "fb_set_serial": (None, [C.c_int]),
     "fb_set_msm_tables": (None, [C.c_int]),
     "fb_set_msm_batch_affine": (None, [C.c_int]),
+    "fb_set_prove_graph": (None, [C.c_int]),
     "fb_kernel_stats_enable": (None, [C.c_int]),
     "fb_kernel_stats_reset": (None, []),
     "fb_kernel_stats": (C.c_int, [C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),

@@ -174,6 +174,9 @@ void fb_set_msm_tables(int mode);
  * kernel on B200), 1 on, 2 on even for small inputs (tests).  Applies to keys loaded
  * afterwards and to fb_test_msm. */
 void fb_set_msm_batch_affine(int on);
+/* Keys with a domain of at most 2^16 replay the device side of a prove as one CUDA graph (captured at the
+ * first prove of the key): 1 on (default; FB_PROVE_GRAPH=0 in the environment turns it off), 0 off. */
+void fb_set_prove_graph(int on);
 void fb_kernel_stats_enable(int on);
 void fb_kernel_stats_reset(void);
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms);
