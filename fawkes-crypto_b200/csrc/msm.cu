@@ -50,6 +50,10 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   int tl = 4;
   while (tl < 8 && (1ull << tl) < want) tl++;
   if (tl < MSM_MIN_TASK_LOG) tl = MSM_MIN_TASK_LOG;
+  if (const char* e = getenv("FB_MSM_TASK_LOG")) {
+    int v = atoi(e);
+    if (v >= MSM_MIN_TASK_LOG && v <= 10) tl = v;
+  }
   p.task_log = tl;
   return p;
 }

@@ -45,6 +45,17 @@ def test_poseidon_circuit_matches_native_and_costs_228_gates():
     assert len(cs.gates) == 8 * 3 * 3 + 53 * 3 - 3 == 228          # SURVEY App. E / README.md:52
 
 
+def test_poseidon_4_8_54_costs_255_gates():
+    """The other Poseidon row of the reference's benchmark table (README.md:48): poseidon hash (4, 8, 54) = 255."""
+    P = fe.PoseidonParams(4, 8, 54)
+    rng = random.Random(6)
+    vals = [rng.randrange(bn.R) for _ in range(3)]
+    cs = fe.BuildCS()
+    out = fe.c_poseidon([cs.alloc(v) for v in vals], P)
+    assert out.value == fe.poseidon(vals, P)
+    assert len(cs.gates) == 255
+
+
 def test_merkle_circuit_shape_is_cfg1():
     rng = random.Random(11)
     leaf = rng.randrange(bn.R)
