@@ -386,6 +386,30 @@ def prove_with_rs(params: Parameters, values_input: np.ndarray, values_aux: np.n
     return (inputs, proof, h) if return_h else (inputs, proof)
 
 
+def prove_batch(params: Parameters, witnesses, rs: Sequence[int], ss: Sequence[int], ctx: Context):
+    """Many proofs of ONE circuit on one resident key (BASELINE configs[1]); the reference proves them one
+    `prove()` call at a time (prover.rs:63-90).  witnesses: sequence of (values_input, values_aux) pairs.
+    Returns [(public inputs, Proof), ...] in order; proof i is byte-identical to
+    prove_with_rs(params, *witnesses[i], rs[i], ss[i])."""
+    count = len(witnesses)
+    if not (count == len(rs) == len(ss)):
+        raise ValueError("prove_batch: witnesses, rs and ss differ in length")
+    if count == 0:
+        return []
+    pk = params.load(ctx, getattr(params, "_checked", True))
+    vis = [np.ascontiguousarray(w[0], dtype=np.uint64) for w in witnesses]
+    vas = [np.ascontiguousarray(w[1], dtype=np.uint64) for w in witnesses]
+    n_in, n_aux = vis[0].shape[0], vas[0].shape[0]
+    if any(v.shape != (n_in, 4) for v in vis) or any(v.shape != (n_aux, 4) for v in vas):
+        raise ValueError("prove_batch: every witness must have the circuit's shape")
+    ins = (C.c_void_p * count)(*[v.ctypes.data for v in vis])
+    axs = (C.c_void_p * count)(*[v.ctypes.data for v in vas])
+    ra, sa = fr_array(list(rs)), fr_array(list(ss))
+    out = np.zeros((count, 256), dtype=np.uint8)
+    nv.check(nv.lib.fb_prove_batch(ctx.handle, pk, count, ins, n_in, axs, n_aux, nv.ptr(ra), nv.ptr(sa), nv.ptr(out)))
+    return [(vis[i][1:].copy(), Proof.from_raw(out[i].tobytes())) for i in range(count)]
+
+
 def prove(params: Parameters, values_input: np.ndarray, values_aux: np.ndarray, ctx: Context):
     """`prove` of prover.rs:63-90: r, s from the OS RNG."""
     return prove_with_rs(params, values_input, values_aux, _sample_fr(), _sample_fr(), ctx)

@@ -79,3 +79,99 @@ def test_merkle_circuit_shape_is_cfg1():
     # first gates: inputize, then the 32 path-bit checks
     assert gates[0] == ([(1, (AUX, 0))], [(1, (INPUT, 0))], [(1, (INPUT, 1))])
     assert gates[1][0] == [(1, (AUX, 34))] and gates[1][2] == []
+
+
+# ---------------------------------------------------------------- configs[1]: EdDSA-Poseidon ---
+def _rand_subgroup_point(jj, rng):
+    """EdwardsPoint::rand (native/ecc.rs:93-100) times the cofactor."""
+    while True:
+        y = rng.randrange(bn.R)
+        y2 = y * y % bn.R
+        x = fe.fr_sqrt((y2 - 1) * pow(jj.d * y2 + 1, -1, bn.R) % bn.R)
+        if x is not None:
+            return fe.ed_mul((x, y), 8, jj.d)
+
+
+def test_jubjub_params_and_generator():
+    jj = fe.JubJubBN256()
+    # engines/bn256/mod.rs:50-56: the Montgomery form of the same curve, u a non-residue
+    assert jj.a == 168698 and jj.b * (1 + jj.d) % bn.R == bn.R - 4
+    assert fe.fr_sqrt(jj.u) is None
+    assert jj.in_curve(jj.g) and jj.g != (0, 1)
+    assert fe.ed_mul(jj.g, fe.FS, jj.d) == (0, 1)                   # prime-order subgroup
+    assert fe.FS_BITS == 251 and fe.R_BITS == 254
+    # Montgomery <-> Edwards round trip, decompress recovers the point from x
+    assert fe.mont_into_edwards(fe.ed_into_montgomery(jj.g)) == jj.g
+    assert jj.subgroup_decompress(jj.g[0]) == jj.g
+    p = fe.ed_mul(jj.g, 12345, jj.d)
+    assert fe.ed_add(p, jj.g, jj.d) == fe.ed_mul(jj.g, 12346, jj.d)
+
+
+def test_eddsa_native_sign_verify():
+    jj, P = fe.JubJubBN256(), fe.PoseidonParams(4, 8, 54)
+    rng = random.Random(21)
+    sk, m = rng.randrange(fe.FS), rng.randrange(bn.R)
+    s, r = fe.eddsaposeidon_sign(sk, m, P, jj)
+    a = fe.ed_mul(jj.g, sk, jj.d)[0]
+    assert fe.eddsaposeidon_verify(s, r, a, m, P, jj)
+    assert not fe.eddsaposeidon_verify(s, r, a, (m + 1) % bn.R, P, jj)
+    assert not fe.eddsaposeidon_verify((s + 1) % fe.FS, r, a, m, P, jj)
+
+
+def test_ecmul_gadgets_cost_what_the_readme_says():
+    """README.md:50-51: ecmul 254 bits = 2,296 constraints, ecmul_const 254 bits = 513 (the shapes of
+    tests/circuit_ecc.rs:153-201); both must also compute the native product."""
+    jj = fe.JubJubBN256()
+    rng = random.Random(22)
+    p, n = _rand_subgroup_point(jj, rng), rng.randrange(bn.R)
+    want = fe.ed_mul(p, n % fe.FS, jj.d)
+    for const_base, cost in ((False, 2296), (True, 513)):
+        cs = fe.BuildCS()
+        sp = fe.CEdwardsPoint.from_const(cs, p) if const_base else fe.CEdwardsPoint.alloc(cs, p)
+        bits = fe.c_into_bits_le_strict(cs.alloc(n))
+        assert [b.value for b in bits] == [(n >> i) & 1 for i in range(254)]
+        g0 = len(cs.gates)
+        res = sp.mul(bits, jj)
+        assert len(cs.gates) - g0 == cost
+        assert (res.x.value, res.y.value) == want
+
+
+def test_bit_gadgets():
+    rng = random.Random(23)
+    for limit, v, ct in ((8, 200, 199), (8, 200, 200), (9, 200, 201), (251, fe.FS - 1, fe.FS - 1), (251, fe.FS, fe.FS - 1)):
+        cs = fe.BuildCS()
+        bits = fe.c_into_bits_le(cs.alloc(v), limit)
+        assert [b.value for b in bits] == [(v >> i) & 1 for i in range(limit)]
+        assert fe.c_comp_constant(bits, ct).value == (1 if v > ct else 0)
+    cs = fe.BuildCS()
+    x = cs.alloc(rng.randrange(1, bn.R))
+    assert fe.c_is_zero(x).value == 0 and fe.c_is_zero(x - x).value == 1 and fe.c_is_zero(cs.alloc(0)).value == 1
+    q = fe.c_div_unchecked(x, cs.alloc(7))
+    assert q.value * 7 % bn.R == x.value
+    cols = [[rng.randrange(bn.R) for _ in range(8)] for _ in range(2)]
+    for idx in range(8):
+        cs = fe.BuildCS()
+        s = [fe.c_alloc_bool(cs, (idx >> j) & 1) for j in range(3)]
+        assert [o.value for o in fe.c_mux3(s, cols)] == [cols[0][idx], cols[1][idx]]
+
+
+def test_eddsa_circuit_shape():
+    """configs[1].  The gadget code at the reference's commit gives 4,121 gates for c_eddsaposeidon_verify
+    (2 x 20 subgroup_decompress + 255 Poseidon + 510 strict bits + 2,296 ecmul + 251 + 253 range-checked
+    s bits + 507 fixed-base mul + 6 add + 3 is_zero); README.md:53 quotes 3,860 (an older gadget set: its
+    19-constraint 'oncurve+subgroup check' row is 25 here too).  With inputize + assert_const + the two
+    bellman input rows: 4,125 rows -> m = 2^13."""
+    rng = random.Random(24)
+    sk, m = rng.randrange(fe.FS), rng.randrange(bn.R)
+    gates, inputs, aux = fe.eddsa_circuit(sk, m)
+    assert len(gates) == 4121 + 2 and inputs == [1, m]
+    w = {(INPUT, i): v for i, v in enumerate(inputs)}
+    w.update({(AUX, i): v for i, v in enumerate(aux)})
+    for A, B, C in gates:
+        ev = [sum(c * w[k] for c, k in lc) % bn.R for lc in (A, B, C)]
+        assert ev[0] * ev[1] % bn.R == ev[2]
+        for lc in (A, B, C):
+            assert [k for _, k in lc] == sorted(k for _, k in lc) and all(c % bn.R for c, _ in lc)
+    # the same circuit for another key and message: identical gate structure (only the witness moves)
+    gates2, _, aux2 = fe.eddsa_circuit(rng.randrange(fe.FS), rng.randrange(bn.R))
+    assert gates2 == gates and aux2 != aux

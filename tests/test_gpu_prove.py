@@ -276,6 +276,50 @@ def test_cfg1_poseidon_merkle_setup_prove_verify(ctx):
     params.unload()
 
 
+def test_cfg2_eddsa_poseidon_batch_setup_prove_verify(ctx):
+    """configs[1]: the EdDSA-Poseidon signature circuit (circuit/eddsaposeidon.rs:16-47; 4,121 + 2 gates at
+    the reference's commit, m = 2^13) built by the front-end restatement, one resident key, several
+    signatures (different keys and messages -> different witnesses and public inputs) proved as one batch.
+    Every batch proof equals the proof-by-proof result and the C++ CPU restatement byte for byte and
+    verifies against its own message only."""
+    import random
+    import fawkes_crypto_b200 as fb
+    import bench
+    from oracle import cpu
+    from oracle import frontend as fe
+    rng = random.Random(2027)
+    jj, P = fe.JubJubBN256(), fe.PoseidonParams(4, 8, 54)
+    count = 6
+    cases = [fe.eddsa_circuit(rng.randrange(fe.FS), rng.randrange(bn.R), P, jj) for _ in range(count)]
+    gates = cases[0][0]
+    assert len(gates) == 4123 and all(c[0] == gates for c in cases)
+    n_aux = len(cases[0][2])
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    circ = fb.Circuit.from_raw_gates(raw, len(gates), 2, n_aux)
+    td, r0, s0 = synth.synth_trapdoor(synth.SEED_BASE + 2)
+    params = fb.setup(circ, ctx, trapdoor=[td.alpha, td.beta, td.gamma, td.delta, td.tau],
+                      gates_blob=codec.brotli_compress(raw))
+    params = fb.Parameters.read(params.write())
+    assert params.info()["log_m"] == 13
+    wit = [(fr_np(inp), fr_np(aux)) for _, inp, aux in cases]
+    rs = [(r0 + 5 * i) % bn.R for i in range(count)]
+    ss = [(s0 + 9 * i) % bn.R for i in range(count)]
+    batch = fb.prove_batch(params, wit, rs, ss, ctx)
+    sh = circ.shape()
+    rp, cl, cf = bench.expand_csr(fb, circ)
+    for i, (inputs, proof) in enumerate(batch):
+        assert fr_list(inputs) == cases[i][1][1:]
+        _, single = fb.prove_with_rs(params, wit[i][0], wit[i][1], rs[i], ss[i], ctx)
+        assert single.to_raw() == proof.to_raw(), i
+        assert fb.verify(params.get_vk(), proof, inputs)
+        assert not fb.verify(params.get_vk(), proof, batch[(i + 1) % count][0])
+        if i < 2:
+            ref, _, _ = cpu.prove(params.bellman_bytes, sh["n_gates"], sh["n_in"], sh["n_aux"], rp, cl, cf,
+                                  wit[i][0], wit[i][1], fb.groth16.fr_raw(rs[i]), fb.groth16.fr_raw(ss[i]), 4)
+            assert proof.to_raw() == ref, i
+    params.unload()
+
+
 def test_prove_2_24_full_size_verifies(ctx):
     """BASELINE configs[3] at full size (2^24 rows, 75 GB resident key with window tables): the proof passes
     the pairing check (a size-independent end-to-end property: A, B and C are right only if all five
