@@ -742,6 +742,13 @@ int fb_init(const int* devices, int ndev, fb_ctx** out) {
   int dev = devices ? devices[0] : 0;
   if (dev < 0 || dev >= n) { set_error("device %d out of range (have %d)", dev, n); return FB_ERR_ARG; }
   FB_CUDA(cudaSetDevice(dev));
+  if (const char* e = getenv("FB_L2_FETCH_BYTES")) {  // device-wide L2 fetch granularity hint (A/B measurements)
+    size_t before = 0, after = 0;
+    cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+    cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "[fawkes_b200] L2 fetch granularity %zu -> %zu bytes\n", before, after);
+  }
   Ctx* c = new Ctx();
   c->device = dev;
   FB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -261,11 +261,38 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
 // lives at index b + t: bucket b owns the contiguous slots b + floor(start_b / T) .. b +
 // floor((end_b - 1) / T), so no second scan is needed to find them.
 // DIRECT: `bases` already holds the points in sorted order (output of the batch-affine rounds).
+#ifndef MSM_LD64_DEFAULT
+#define MSM_LD64_DEFAULT 1
+#endif
+static int msm_ld64() {  // FB_MSM_LD64=0 restores plain loads (A/B measurements)
+  static const int v = [] { const char* e = getenv("FB_MSM_LD64"); return e ? atoi(e) : MSM_LD64_DEFAULT; }();
+  return v;
+}
+
+// A base is gathered from a random place of a multi-gigabyte array.  A plain load lets L2 fetch a whole
+// 128-byte line for a 64-byte G1 point (ncu at 2^24: 29.3 GB of DRAM reads for 14.8 GB of points);
+// the .L2::64B prefetch-size hint asks for the two sectors that are used.
+template <class F>
+__device__ __forceinline__ Affine<F> load_base(const Affine<F>* __restrict__ p, int ld64) {
+  if (sizeof(Affine<F>) == 64 && ld64) {
+    Affine<F> r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(d[i].x), "=r"(d[i].y), "=r"(d[i].z), "=r"(d[i].w)
+                   : "l"(s + i));
+    return r;
+  }
+  return *p;
+}
+
 template <class F, bool DIRECT>
 __global__ void __launch_bounds__(128, MSM_ACC_MIN_CTAS(F))
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
-             XYZZ<F>* __restrict__ partials) {
+             XYZZ<F>* __restrict__ partials, int ld64) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t total = offsets[nb];
   const uint32_t start = t << task_log;
@@ -286,7 +313,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
   constexpr bool REG_PREFETCH = sizeof(F) == sizeof(Fq);
   uint32_t e = DIRECT ? 0u : sorted[start];
   Affine<F> nxt;
-  if (REG_PREFETCH) nxt = DIRECT ? bases[start] : bases[e & 0x7fffffffu];
+  if (REG_PREFETCH) nxt = DIRECT ? bases[start] : load_base(bases + (e & 0x7fffffffu), ld64);
   for (uint32_t p = start; p < end; p++) {
     if (p >= bend) {  // bucket boundary: flush and move on (empty buckets are skipped)
       partials[b + t] = acc;
@@ -302,7 +329,7 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
           nxt = bases[p + 1];
         } else {
           e = sorted[p + 1];
-          nxt = bases[e & 0x7fffffffu];
+          nxt = load_base(bases + (e & 0x7fffffffu), ld64);
         }
       }
     } else {
@@ -786,10 +813,10 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   cudaMemsetAsync(s.heavy, 0, 4, st);
   if (R > 0)
     k_accumulate<F, true><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, offsets, nb,
-                                                                                task_log, partials);
+                                                                                task_log, partials, 0);
   else
     k_accumulate<F, false><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb,
-                                                                                 p.task_log, partials);
+                                                                                 p.task_log, partials, msm_ld64());
   kstat_end(kind, st);
   count_launch(reuse_sort ? 5 : 10);
   k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, offsets, nb, task_log, buckets, s.heavy);

@@ -300,11 +300,11 @@ def test_cfg2_eddsa_poseidon_batch_setup_prove_verify(ctx):
     params = fb.setup(circ, ctx, trapdoor=[td.alpha, td.beta, td.gamma, td.delta, td.tau],
                       gates_blob=codec.brotli_compress(raw))
     params = fb.Parameters.read(params.write())
-    assert params.info()["log_m"] == 13
     wit = [(fr_np(inp), fr_np(aux)) for _, inp, aux in cases]
     rs = [(r0 + 5 * i) % bn.R for i in range(count)]
     ss = [(s0 + 9 * i) % bn.R for i in range(count)]
     batch = fb.prove_batch(params, wit, rs, ss, ctx)
+    assert params.info()["log_m"] == 13
     sh = circ.shape()
     rp, cl, cf = bench.expand_csr(fb, circ)
     for i, (inputs, proof) in enumerate(batch):
