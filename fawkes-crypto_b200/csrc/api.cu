@@ -3,8 +3,13 @@
 #include "../../include/fawkes_b200.h"
 
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <future>
+#include <map>
+#include <mutex>
+#include <set>
 #include <thread>
 
 #include "internal.h"
@@ -796,6 +801,33 @@ int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_
   return fb_circuit_from_raw_gates(raw.data(), raw.size(), num_gates, n_in, n_aux, out);
 }
 
+int fb_circuit_from_raw_gates_gpu(fb_ctx* ctx, const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
+                                  uint32_t n_aux, fb_circuit** out, float* times_ms) {
+  if (!ctx || !out || (!gates && len)) { set_error("fb_circuit_from_raw_gates_gpu: bad argument"); return FB_ERR_ARG; }
+  Circuit* c = new Circuit();
+  c->n_in = n_in;
+  c->n_aux = n_aux;
+  int rc = parse_gates_device(reinterpret_cast<Ctx*>(ctx), gates, len, n_in, n_aux, c->csr, times_ms);
+  if (rc) { delete c; return rc; }
+  if (c->csr.n_gates != num_gates) {
+    set_error("gate stream holds %u gates, Parameters announce %u", c->csr.n_gates, num_gates);
+    delete c;
+    return FB_ERR_FORMAT;
+  }
+  *out = reinterpret_cast<fb_circuit*>(c);
+  return FB_OK;
+}
+
+int fb_circuit_from_gates_gpu(fb_ctx* ctx, const uint8_t* gates_brotli, size_t len, uint32_t num_gates, uint32_t n_in,
+                              uint32_t n_aux, fb_circuit** out, float* times_ms) {
+  std::vector<uint8_t> raw;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = brotli_decode(gates_brotli, len, raw);
+  if (rc) return rc;
+  if (times_ms) times_ms[4] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  return fb_circuit_from_raw_gates_gpu(ctx, raw.data(), raw.size(), num_gates, n_in, n_aux, out, times_ms);
+}
+
 void fb_circuit_free(fb_circuit* c) { delete reinterpret_cast<Circuit*>(c); }
 
 int fb_circuit_shape(const fb_circuit* c_, uint32_t* n_in, uint32_t* n_aux, uint32_t* n_gates,
@@ -827,7 +859,7 @@ int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uin
   int rc = parse_params(bellman_params, len, v);
   if (rc) return rc;
   fb_circuit* c = nullptr;
-  rc = fb_circuit_from_gates(gates_brotli, glen, num_gates, v.n_ic, v.n_l, &c);
+  rc = fb_circuit_from_gates_gpu(ctx, gates_brotli, glen, num_gates, v.n_ic, v.n_l, &c, nullptr);
   if (rc) return rc;
   rc = fb_pk_load_circuit(ctx, bellman_params, len, c, checked, out);
   fb_circuit_free(c);
@@ -961,6 +993,168 @@ int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* cons
   for (int t = 0; t < K; t++)
     if (rcs[t]) { set_error("%s", errs[t].c_str()); return rcs[t]; }
   return FB_OK;
+}
+
+// ---- streaming proves ------------------------------------------------
+// The reference's prove() is synchronous: witness generation (prover.rs:69-76, host, single thread) and
+// create_random_proof (prover.rs:78-80) alternate, so the prover idles while the next witness is made.
+// A stream keeps up to `depth` submitted proofs queued or running on the key's batch slots; submit copies
+// the witness and returns, so the caller generates witness k+1 while proof k runs, and collects proofs by
+// ticket in any order.  Proof bytes are those of fb_prove on the same arguments.
+struct ProveStream {
+  struct Job {
+    uint64_t ticket;
+    int buf;  // index of the pinned witness buffer [inputs | aux] this proof reads
+    uint64_t r[4], s[4];
+  };
+  struct Result {
+    int rc = FB_OK;
+    std::string err;
+    uint8_t proof[256];
+  };
+  Ctx* c0 = nullptr;
+  ProvingKey* pk = nullptr;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done, cv_space;
+  std::deque<Job> queue;
+  std::map<uint64_t, Result> done;
+  std::set<uint64_t> outstanding;  // submitted and not collected yet
+  uint64_t next_ticket = 1;
+  size_t in_flight = 0, depth = 1;
+  bool closing = false;
+  std::vector<std::thread> workers;
+  // one pinned witness buffer per proof that can be queued or running: submit is a plain memcpy (no page
+  // faults) and the upload inside the prove is a real asynchronous DMA
+  std::vector<uint64_t*> bufs;
+  std::vector<int> free_bufs;
+
+  void run(int t) {
+    ProvingKey* p = t == 0 ? pk : pk->slots[t - 1];
+    Ctx* c = t == 0 ? c0 : p->ctx;
+    cudaSetDevice(c0->device);
+    for (;;) {
+      Job job;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return closing || !queue.empty(); });
+        if (queue.empty()) return;  // closing
+        job = queue.front();
+        queue.pop_front();
+      }
+      Result res;
+      const uint64_t* w = bufs[job.buf];
+      res.rc = prove_impl(c, p, w, pk->n_in, pk->n_aux ? w + 4 * (size_t)pk->n_in : nullptr, pk->n_aux, nullptr, job.r,
+                          job.s, res.proof, nullptr, nullptr);
+      if (res.rc) res.err = last_error_cstr();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        done.emplace(job.ticket, std::move(res));
+        free_bufs.push_back(job.buf);
+        in_flight--;
+      }
+      cv_done.notify_all();
+      cv_space.notify_all();
+    }
+  }
+};
+
+int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
+  ProvingKey* pk = reinterpret_cast<ProvingKey*>(pk_);
+  Ctx* c0 = reinterpret_cast<Ctx*>(ctx);
+  if (!pk || !c0 || !out) { set_error("fb_stream_open: null handle"); return FB_ERR_ARG; }
+  if (pk->nshards != 1 || pk->dist_g) { set_error("fb_stream_open on a sharded key"); return FB_ERR_ARG; }
+  int want = 8;
+  if (const char* e = getenv("FB_BATCH_SLOTS")) want = std::max(1, std::min(32, atoi(e)));
+  if (pk->m > (1u << 16) || g_serial) want = 1;  // a big prove fills the GPU on its own (fb_prove_batch)
+  FB_CUDA(cudaSetDevice(c0->device));
+  while ((int)pk->slots.size() + 1 < want) {
+    ProvingKey* sl = make_slot(pk);
+    if (!sl) break;
+    pk->slots.push_back(sl);
+  }
+  const int K = std::min<int>(want, (int)pk->slots.size() + 1);
+  ProveStream* st = new ProveStream();
+  st->c0 = c0;
+  st->pk = pk;
+  st->depth = (size_t)std::max(depth > 0 ? depth : 2 * K, 1);
+  const size_t wbytes = std::max<size_t>(((size_t)pk->n_in + pk->n_aux) * sizeof(Fr), 32);
+  for (size_t i = 0; i < st->depth; i++) {
+    void* b = nullptr;
+    if (cudaMallocHost(&b, wbytes) != cudaSuccess) {
+      cudaGetLastError();
+      for (uint64_t* q : st->bufs) cudaFreeHost(q);
+      delete st;
+      set_error("fb_stream_open: cannot pin %zu bytes per queued witness", wbytes);
+      return FB_ERR_CUDA;
+    }
+    st->bufs.push_back(reinterpret_cast<uint64_t*>(b));
+    st->free_bufs.push_back((int)i);
+  }
+  for (int t = 0; t < K; t++) st->workers.emplace_back([st, t] { st->run(t); });
+  *out = reinterpret_cast<fb_stream*>(st);
+  return FB_OK;
+}
+
+int fb_stream_submit(fb_stream* st_, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux, uint32_t n_aux,
+                     const uint64_t r[4], const uint64_t s[4], uint64_t* ticket) {
+  ProveStream* st = reinterpret_cast<ProveStream*>(st_);
+  if (!st || !inputs || (!aux && n_aux) || !r || !s || !ticket) { set_error("fb_stream_submit: bad argument"); return FB_ERR_ARG; }
+  if (n_in != st->pk->n_in || n_aux != st->pk->n_aux) {
+    set_error("witness has n_in=%u n_aux=%u, key expects %u / %u", n_in, n_aux, st->pk->n_in, st->pk->n_aux);
+    return FB_ERR_ARG;
+  }
+  ProveStream::Job job;
+  memcpy(job.r, r, 32);
+  memcpy(job.s, s, 32);
+  {
+    std::unique_lock<std::mutex> lk(st->mu);
+    st->cv_space.wait(lk, [&] { return st->in_flight < st->depth; });
+    job.buf = st->free_bufs.back();  // in_flight < depth == number of buffers: one is free
+    st->free_bufs.pop_back();
+    job.ticket = *ticket = st->next_ticket++;
+    st->in_flight++;
+    st->outstanding.insert(job.ticket);
+  }
+  // the copy runs outside the lock: the buffer is owned by this job until its proof is done
+  uint64_t* w = st->bufs[job.buf];
+  memcpy(w, inputs, (size_t)n_in * 32);
+  if (n_aux) memcpy(w + 4 * (size_t)n_in, aux, (size_t)n_aux * 32);
+  {
+    std::lock_guard<std::mutex> lk(st->mu);
+    st->queue.push_back(job);
+  }
+  st->cv_job.notify_one();
+  return FB_OK;
+}
+
+int fb_stream_wait(fb_stream* st_, uint64_t ticket, uint8_t proof_raw[256]) {
+  ProveStream* st = reinterpret_cast<ProveStream*>(st_);
+  if (!st || !proof_raw) { set_error("fb_stream_wait: bad argument"); return FB_ERR_ARG; }
+  std::unique_lock<std::mutex> lk(st->mu);
+  if (!st->outstanding.count(ticket)) { set_error("fb_stream_wait: unknown or already collected ticket"); return FB_ERR_ARG; }
+  st->cv_done.wait(lk, [&] { return st->done.count(ticket) != 0; });
+  st->outstanding.erase(ticket);
+  ProveStream::Result res = std::move(st->done[ticket]);
+  st->done.erase(ticket);
+  lk.unlock();
+  if (res.rc) { set_error("%s", res.err.c_str()); return res.rc; }
+  memcpy(proof_raw, res.proof, 256);
+  return FB_OK;
+}
+
+void fb_stream_close(fb_stream* st_) {
+  ProveStream* st = reinterpret_cast<ProveStream*>(st_);
+  if (!st) return;
+  {
+    std::lock_guard<std::mutex> lk(st->mu);
+    st->closing = true;
+    st->in_flight -= st->queue.size();
+    st->queue.clear();  // proofs not started yet are dropped
+  }
+  st->cv_job.notify_all();
+  for (auto& t : st->workers) t.join();
+  for (uint64_t* b : st->bufs) cudaFreeHost(b);
+  delete st;
 }
 
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],

@@ -133,6 +133,10 @@ int parse_params(const uint8_t* b, size_t len, ParamsView& v);  // api.cu
 int parse_gates_to_csr(const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out);
 int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out);
 int upload_csr(const HostCsr& h, DevCsr& d, cudaStream_t st);
+// ingest.cu: the same CSR with the per-term work (parse, range checks, Montgomery form, dictionary) on the GPU
+struct Ctx;
+int parse_gates_device(Ctx* ctx, const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out,
+                       float* times_ms);
 void free_csr(DevCsr& d);
 int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, bool checked, cudaStream_t st);
 int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, bool checked, cudaStream_t st);

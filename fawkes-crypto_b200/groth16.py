@@ -82,16 +82,32 @@ class Circuit:
         self.handle = handle
 
     @classmethod
-    def from_gates_blob(cls, blob: bytes, num_gates: int, n_in: int, n_aux: int) -> "Circuit":
+    def from_gates_blob(cls, blob: bytes, num_gates: int, n_in: int, n_aux: int, ctx: "Context" = None) -> "Circuit":
+        """`Parameters.2` (brotli of the borsh gate stream).  With a Context the per-term work runs on the GPU
+        (fb_circuit_from_gates_gpu; `ingest_ms` then holds the stage times); both build the same circuit."""
         h = C.c_void_p()
-        nv.check(nv.lib.fb_circuit_from_gates(nv.ptr(blob), len(blob), num_gates, n_in, n_aux, C.byref(h)))
-        return cls(h)
+        if ctx is None:
+            nv.check(nv.lib.fb_circuit_from_gates(nv.ptr(blob), len(blob), num_gates, n_in, n_aux, C.byref(h)))
+            return cls(h)
+        ms = (C.c_float * 6)()
+        nv.check(nv.lib.fb_circuit_from_gates_gpu(ctx.handle, nv.ptr(blob), len(blob), num_gates, n_in, n_aux,
+                                                  C.byref(h), ms))
+        c = cls(h)
+        c.ingest_ms = dict(zip(("frame", "upload", "kernels", "download", "brotli", "alloc"), [float(x) for x in ms]))
+        return c
 
     @classmethod
-    def from_raw_gates(cls, raw: bytes, num_gates: int, n_in: int, n_aux: int) -> "Circuit":
+    def from_raw_gates(cls, raw: bytes, num_gates: int, n_in: int, n_aux: int, ctx: "Context" = None) -> "Circuit":
         h = C.c_void_p()
-        nv.check(nv.lib.fb_circuit_from_raw_gates(nv.ptr(raw), len(raw), num_gates, n_in, n_aux, C.byref(h)))
-        return cls(h)
+        if ctx is None:
+            nv.check(nv.lib.fb_circuit_from_raw_gates(nv.ptr(raw), len(raw), num_gates, n_in, n_aux, C.byref(h)))
+            return cls(h)
+        ms = (C.c_float * 6)()
+        nv.check(nv.lib.fb_circuit_from_raw_gates_gpu(ctx.handle, nv.ptr(raw), len(raw), num_gates, n_in, n_aux,
+                                                      C.byref(h), ms))
+        c = cls(h)
+        c.ingest_ms = dict(zip(("frame", "upload", "kernels", "download", "brotli", "alloc"), [float(x) for x in ms]))
+        return c
 
     @classmethod
     def synthetic(cls, n_rows: int, seed: int) -> "Circuit":
@@ -303,9 +319,9 @@ class Parameters:
         return VK(_g1_from_be(b[0:64]), _g2_from_be(b[128:256]), _g2_from_be(b[256:384]),
                   _g2_from_be(b[448:576]), [_g1_from_be(b[580 + 64 * i:644 + 64 * i]) for i in range(n_ic)])
 
-    def circuit(self) -> Circuit:
+    def circuit(self, ctx: "Context" = None) -> Circuit:
         if self._circuit is None:
-            self._circuit = Circuit.from_gates_blob(self.gates_blob, self.num_gates, self.n_in, self.n_aux)
+            self._circuit = Circuit.from_gates_blob(self.gates_blob, self.num_gates, self.n_in, self.n_aux, ctx)
         return self._circuit
 
     def load(self, ctx: Context, checked: bool = True, shard: int = 0, nshards: int = 1):
@@ -313,7 +329,7 @@ class Parameters:
         if self._pk is None:
             h = C.c_void_p()
             nv.check(nv.lib.fb_pk_load_shard(ctx.handle, nv.ptr(self.bellman_bytes), len(self.bellman_bytes),
-                                             self.circuit().handle, int(checked), shard, nshards, C.byref(h)))
+                                             self.circuit(ctx).handle, int(checked), shard, nshards, C.byref(h)))
             self._pk, self._pk_ctx = h, ctx
         return self._pk
 
@@ -408,6 +424,52 @@ def prove_batch(params: Parameters, witnesses, rs: Sequence[int], ss: Sequence[i
     out = np.zeros((count, 256), dtype=np.uint8)
     nv.check(nv.lib.fb_prove_batch(ctx.handle, pk, count, ins, n_in, axs, n_aux, nv.ptr(ra), nv.ptr(sa), nv.ptr(out)))
     return [(vis[i][1:].copy(), Proof.from_raw(out[i].tobytes())) for i in range(count)]
+
+
+class ProveStream:
+    """Streaming proves on one resident key (fb_stream_*): `submit` copies the witness and returns a ticket,
+    so the caller builds witness k+1 (the circuit closure re-run of prover.rs:69-76) while proof k is on the
+    GPU; `wait(ticket)` returns (public inputs, Proof), byte-identical to prove_with_rs on the same arguments.
+    While the stream is open the key is used through it only."""
+
+    def __init__(self, params: Parameters, ctx: Context, depth: int = 0):
+        self._pk = params.load(ctx, getattr(params, "_checked", True))
+        self._params = params
+        self._h = C.c_void_p()
+        self._inputs = {}
+        nv.check(nv.lib.fb_stream_open(ctx.handle, self._pk, depth, C.byref(self._h)))
+
+    def submit(self, values_input: np.ndarray, values_aux: np.ndarray, r: int, s: int) -> int:
+        vi = np.ascontiguousarray(values_input, dtype=np.uint64)
+        va = np.ascontiguousarray(values_aux, dtype=np.uint64)
+        ra, sa = fr_raw(r), fr_raw(s)
+        t = C.c_uint64()
+        nv.check(nv.lib.fb_stream_submit(self._h, nv.ptr(vi), vi.shape[0], nv.ptr(va), va.shape[0], nv.ptr(ra), nv.ptr(sa),
+                                         C.byref(t)))
+        self._inputs[t.value] = vi[1:].copy()
+        return t.value
+
+    def wait(self, ticket: int):
+        out = np.zeros(256, dtype=np.uint8)
+        nv.check(nv.lib.fb_stream_wait(self._h, ticket, nv.ptr(out)))
+        return self._inputs.pop(ticket), Proof.from_raw(out.tobytes())
+
+    def close(self):
+        if self._h:
+            nv.lib.fb_stream_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def prove(params: Parameters, values_input: np.ndarray, values_aux: np.ndarray, ctx: Context):

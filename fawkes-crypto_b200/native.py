@@ -43,6 +43,8 @@ SIGNATURES = {
     "fb_free": (None, [vp]),
     "fb_circuit_from_gates": (C.c_int, [vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "fb_circuit_from_raw_gates": (C.c_int, [vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "fb_circuit_from_gates_gpu": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), f32p]),
+    "fb_circuit_from_raw_gates_gpu": (C.c_int, [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp), f32p]),
     "fb_circuit_free": (None, [vp]),
     "fb_circuit_shape": (C.c_int, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "fb_pk_load": (C.c_int, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(vp)]),
@@ -52,6 +54,10 @@ SIGNATURES = {
     "fb_pk_get_info": (C.c_int, [vp, C.POINTER(PkInfo)]),
     "fb_prove": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp, vp]),
     "fb_prove_batch": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32, vp, vp, vp]),
+    "fb_stream_open": (C.c_int, [vp, vp, C.c_int, C.POINTER(vp)]),
+    "fb_stream_submit": (C.c_int, [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]),
+    "fb_stream_wait": (C.c_int, [vp, C.c_uint64, vp]),
+    "fb_stream_close": (None, [vp]),
     "fb_prove_device": (C.c_int, [vp, vp, vp, vp, vp, vp]),
     "fb_prove_partial": (C.c_int, [vp, vp, vp, C.c_uint32, vp, C.c_uint32, vp]),
     "fb_prove_finish": (C.c_int, [vp, C.c_size_t, vp, C.c_int, vp, vp, vp]),

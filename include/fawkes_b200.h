@@ -90,6 +90,16 @@ int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_
 /* same, from the un-compressed borsh gate stream */
 int fb_circuit_from_raw_gates(const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
                               uint32_t n_aux, fb_circuit** out);
+/* The same parse with the per-term work on the GPU (what WitnessCS::get_gate_iterator + GateStreamedIterator
+ * redo on every prove, cs.rs:184-223,248-250: 37-byte terms, "Wrong raw integer" check, canonical -> Montgomery
+ * multiply; here once per key, as kernels).  brotli and the walk over the length prefixes stay on the host.
+ * Builds the identical circuit (same CSR, same coefficient dictionary in first-appearance order).
+ * times_ms: optional float[6] = framing walk, blob upload, kernels, copy back, brotli, device allocation (ms).
+ * fb_pk_load uses this path. */
+int fb_circuit_from_gates_gpu(fb_ctx* ctx, const uint8_t* gates_brotli, size_t len, uint32_t num_gates,
+                              uint32_t n_in, uint32_t n_aux, fb_circuit** out, float* times_ms);
+int fb_circuit_from_raw_gates_gpu(fb_ctx* ctx, const uint8_t* gates, size_t len, uint32_t num_gates,
+                                  uint32_t n_in, uint32_t n_aux, fb_circuit** out, float* times_ms);
 void fb_circuit_free(fb_circuit* c);
 int fb_circuit_shape(const fb_circuit* c, uint32_t* n_in, uint32_t* n_aux, uint32_t* n_gates,
                      uint64_t* nnz);
@@ -118,6 +128,18 @@ int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, cons
 int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
                    const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
                    uint8_t* proofs_raw);
+/* Streaming proves on one resident key: the reference's prove() alternates witness generation
+ * (prover.rs:69-76) and create_random_proof (prover.rs:78-80) on one thread; here submit copies the witness
+ * and returns (it blocks only while `depth` proofs are already queued or running; depth <= 0 picks a default),
+ * so witness k+1 is generated while proof k runs.  wait blocks until that proof is done and hands out the
+ * same bytes fb_prove would; tickets may be collected in any order, each once.  While a stream is open the
+ * key must be used through it only.  close drops proofs that have not started. */
+typedef struct fb_stream fb_stream;
+int fb_stream_open(fb_ctx* ctx, fb_pk* pk, int depth, fb_stream** out);
+int fb_stream_submit(fb_stream* st, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux, uint32_t n_aux,
+                     const uint64_t r[4], const uint64_t s[4], uint64_t* ticket);
+int fb_stream_wait(fb_stream* st, uint64_t ticket, uint8_t proof_raw[256]);
+void fb_stream_close(fb_stream* st);
 /* Same, host buffers already on the device (dev_w = [inputs | aux] as Num<Fr>). */
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
                     const uint64_t s[4], uint8_t proof_raw[256]);

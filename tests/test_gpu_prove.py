@@ -222,6 +222,44 @@ def test_prove_batch_matches_single_proofs(ctx):
     params.unload()
 
 
+def test_prove_stream_matches_single_proofs(ctx):
+    """fb_stream_* (witness k+1 is prepared while proof k runs): every proof equals the oracle's, tickets can be
+    collected out of order, a ticket is good once, a wrong-shaped witness is refused at submit."""
+    import fawkes_crypto_b200 as fb
+    seed = synth.SEED_BASE + 6000
+    gates, inp, aux = synth.synth_circuit(400, seed)
+    td, r0, s0 = synth.synth_trapdoor(seed)
+    P = og.setup(gates, 2, len(aux), td)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
+    wi, wa = fr_np(inp), fr_np(aux)
+    count = 12
+    rs = [((r0 + 3 * i) % bn.R, (s0 + 13 * i) % bn.R) for i in range(count)]
+    with fb.ProveStream(params, ctx, depth=3) as st:       # depth < count: submit has to wait for space
+        tickets = []
+        for r, s in rs:
+            scratch_i, scratch_a = wi.copy(), wa.copy()
+            tickets.append(st.submit(scratch_i, scratch_a, r, s))
+            scratch_i[:] = 0                                 # the caller's buffers are free again after submit
+            scratch_a[:] = 0
+        assert len(set(tickets)) == count
+        got = {}
+        for i in reversed(range(count)):
+            inputs, proof = st.wait(tickets[i])
+            assert fr_list(inputs) == inp[1:]
+            got[i] = proof.to_raw()
+        with pytest.raises(fb.native.FbError):
+            st.wait(tickets[0])
+        with pytest.raises(fb.native.FbError):
+            st.submit(wi, wa[:-1], r0, s0)
+    for i in (0, 5, count - 1):
+        assert got[i] == codec.proof_raw(og.prove(P, gates, inp, aux, rs[i][0], rs[i][1])), i
+    # the key is usable again after the stream is closed
+    _, proof = fb.groth16.prove_with_rs(params, wi, wa, rs[1][0], rs[1][1], ctx)
+    assert proof.to_raw() == got[1]
+    params.unload()
+
+
 def test_prove_2_20_bytes_equal_cpp_oracle(ctx):
     """Full BASELINE size (configs[2], 2^20 rows): the GPU proof is byte-identical to the C++ CPU
     restatement (itself byte-checked against the Python oracle in tests/test_oracle.py) and verifies."""
