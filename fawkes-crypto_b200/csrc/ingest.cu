@@ -312,7 +312,7 @@ static uint32_t frame_gates(const uint8_t* raw, size_t len, uint32_t max_gates, 
   return gates;
 }
 
-// times_ms (optional, 6 entries): framing walk on the host, blob upload (concurrent with the walk), kernels, copy back, [4] unused here
+// times_ms (optional, 6 entries): framing walk on the host and, concurrently, blob upload; kernels; copy back, [4] unused here
 // (brotli, filled by the caller), cudaMalloc time
 int parse_gates_device(Ctx* ctx, const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out,
                        float* times_ms) {
@@ -320,33 +320,32 @@ int parse_gates_device(Ctx* ctx, const uint8_t* raw, size_t len, uint32_t n_in, 
   FB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   double t0 = now_s();
-  // the blob goes up on a helper thread while this one walks the length prefixes
+  // the length prefixes are walked on a helper thread (plain CPU work) while this one uploads the blob.
+  // (The other way round -- CUDA calls on a short-lived helper thread -- made the first cudaMalloc after
+  // the thread's exit take ~140 ms in two of three runs.)
   DevBuf d_raw;
   const size_t raw_words = (len + 3) / 4 + 3;  // read_term touches up to 11 words from an aligned base
   float t_up = 0, t_kern = 0, t_down = 0;
-  double t_alloc = 0, ta = 0;
-  cudaError_t up_err = cudaSuccess;
-  std::thread uploader;
-  if (len) {
-    FB_CUDA(d_raw.alloc(raw_words * 4));
-    auto upload = [&, dev = ctx->device] {
-      const double u0 = now_s();
-      up_err = cudaSetDevice(dev);
-      if (up_err == cudaSuccess) up_err = cudaMemset(d_raw.as<uint8_t>() + (len / 4) * 4, 0, raw_words * 4 - (len / 4) * 4);
-      if (up_err == cudaSuccess) up_err = cudaMemcpy(d_raw.p, raw, len, cudaMemcpyHostToDevice);
-      t_up = (float)((now_s() - u0) * 1e3);
-    };
-    const char* seq = getenv("FB_INGEST_SEQ");  // A/B switch: upload before the walk instead of beside it
-    if (seq && atoi(seq)) upload();
-    else uploader = std::thread(upload);
-  }
+  double t_alloc = 0, ta = 0, t_frame = 0;
   std::vector<uint64_t> gstart;
   bool overflow = false;
-  uint32_t n_gates = frame_gates(raw, len, 0xffffffffu, gstart, out.rowptr, &overflow);
-  const double t_frame = now_s() - t0;
-  if (uploader.joinable()) uploader.join();
-  if (overflow) { set_error("gate stream holds 2^30 or more terms in one matrix"); return FB_ERR_FORMAT; }
+  uint32_t n_gates = 0;
+  std::thread walker([&] {
+    n_gates = frame_gates(raw, len, 0xffffffffu, gstart, out.rowptr, &overflow);
+    t_frame = now_s() - t0;
+  });
+  cudaError_t up_err = cudaSuccess;
+  if (len) {
+    up_err = d_raw.alloc(raw_words * 4);
+    if (up_err == cudaSuccess)
+      up_err = cudaMemsetAsync(d_raw.as<uint8_t>() + (len / 4) * 4, 0, raw_words * 4 - (len / 4) * 4, st);
+    if (up_err == cudaSuccess) up_err = cudaMemcpyAsync(d_raw.p, raw, len, cudaMemcpyHostToDevice, st);
+    if (up_err == cudaSuccess) up_err = cudaStreamSynchronize(st);
+    t_up = (float)((now_s() - t0) * 1e3);
+  }
+  walker.join();
   FB_CUDA(up_err);
+  if (overflow) { set_error("gate stream holds 2^30 or more terms in one matrix"); return FB_ERR_FORMAT; }
 
   for (int attempt = 0; attempt < 2 && n_gates; attempt++) {
     t0 = now_s();
