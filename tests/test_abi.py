@@ -94,6 +94,27 @@ def test_gate_stream_parsing_and_errors():
     assert c0.shape()["n_gates"] == 0
 
 
+def test_host_parser_equals_python_parse_on_random_streams():
+    """The host parser is the yardstick of the GPU ingest (tests/test_gpu_ingest.py): check it term by term
+    against the Python restatement of the stream format (oracle codec, cs.rs:184-223) on random streams
+    with repeated, +1, -1 and fresh coefficients and ragged LC lengths."""
+    import bench
+    import fawkes_crypto_b200 as fb
+    from tests.util import random_gate_blob
+    for n_gates, terms in ((1, (3, 2, 1)), (64, (5, 0, 4)), (300, (3, 3, 1))):
+        raw = random_gate_blob(n_gates, 3, 40, seed=n_gates, terms=terms)
+        ref = codec.parse_gates(raw)
+        assert len(ref) == n_gates
+        c = fb.Circuit.from_raw_gates(raw, n_gates, 3, 40)
+        rp, cl, cf = bench.expand_csr(fb, c)
+        for m in range(3):
+            want_cols = [(idx if tag == 0 else 3 + idx) for g in ref for _, (tag, idx) in g[m]]
+            want_coef = [cc for g in ref for cc, _ in g[m]]
+            assert list(rp[m]) == [0] + list(np.cumsum([len(g[m]) for g in ref]))
+            assert list(cl[m]) == want_cols
+            assert fr_list(cf[m]) == want_coef
+
+
 @pytest.fixture(scope="module")
 def golden():
     return json.load(open(os.path.join(ROOT, "tests", "golden", "synth_rows40.json")))
