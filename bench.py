@@ -400,17 +400,18 @@ def run_ours(args):
     imad = C.c_double()
     fb.native.check(lib.fb_probe_imad(ctx.handle, C.byref(imad)))
     ach_mac = per_launch_adds * MAC32_PER_MIXED_ADD / (avg_ms * 1e-3) if avg_ms else 0.0
-    # DRAM traffic of one launch: dram__bytes_read.sum + dram__bytes_write.sum, mean of the four G1 launches
-    # of a 2^24-row prove (profiles/r01_k_accumulate_traffic_2e24.txt: ncu on the serial schedule, with the
-    # .L2::64B loads that are now the default; plain loads moved 25.8e9 bytes per launch)
-    traffic = {24: 13.74e9}.get(args.log_rows) if world == 1 else None
+    # DRAM traffic of one launch: dram__bytes_read.sum + dram__bytes_write.sum, mean of the four G1 launches of
+    # one prove on the serial schedule, with the .L2::64B loads that are now the default --
+    # 2^24: profiles/r01_k_accumulate_traffic_2e24.txt (single-pass metrics; plain loads moved 25.8e9 bytes);
+    # 2^20: profiles/r01_k_accumulate.txt (`ncu --set full` capture; plain loads moved 1.80e9 bytes)
+    traffic = {20: 1.005e9, 24: 13.74e9}.get(args.log_rows) if world == 1 else None
     roofline = {"kernel": "k_accumulate<Fq> (G1 bucket accumulation)", "bound": "hbm", "achieved": ach_gbs,
                 "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / peaks["hbm_gbs"], "traffic": traffic,
                 "peak_source": peaks["source"], "avg_launch_ms": avg_ms, "launches_timed": g1["launches"],
                 "algorithmic_bytes_per_launch": per_launch_adds * BYTES_PER_MIXED_ADD_G1,
                 "note": "algorithmic bytes = (64 B base + 4 B index) x n x W digits; traffic = dram read+write bytes of "
-                        "one launch (ncu, 2^24 capture only; 1.06x the algorithmic bytes since the base gathers carry "
-                        "the .L2::64B hint, 1.99x before); the kernel is integer-pipe bound, see roofline_imad"}
+                        "one launch (ncu captures at 2^20 and 2^24; ~1.06x the algorithmic bytes since the base gathers carry "
+                        "the .L2::64B hint, ~1.9x before); the kernel is integer-pipe bound, see roofline_imad"}
     roofline_imad = {"kernel": roofline["kernel"], "bound": "imad", "achieved": ach_mac / 1e12,
                      "peak": imad.value / 1e12, "unit": "T MAC32/s", "frac": ach_mac / imad.value if imad.value else None,
                      "peak_source": "measured live: independent IMAD.WIDE.U32 accumulate streams, SASS-verified "
