@@ -175,3 +175,27 @@ def test_eddsa_circuit_shape():
     # the same circuit for another key and message: identical gate structure (only the witness moves)
     gates2, _, aux2 = fe.eddsa_circuit(rng.randrange(fe.FS), rng.randrange(bn.R))
     assert gates2 == gates and aux2 != aux
+
+
+def test_frontend_oracle_chain_matches_committed_golden():
+    """tests/golden/frontend_circuits.json (tools/gen_golden_frontend.py): front end -> Python setup (fixed
+    trapdoor) -> C++ prove (fixed r, s) -> independent pairing check, for the EdDSA circuit; the digests of the
+    gate stream and of the bellman Parameters and the 256 proof bytes must be the committed ones."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_golden_frontend as gg
+    golden = json.load(open(os.path.join(root, "tests", "golden", "frontend_circuits.json")))
+    assert set(golden) == {"cfg1_poseidon_merkle", "cfg2_eddsa_poseidon"}
+    got = gg.oracle_chain("cfg2_eddsa_poseidon")
+    assert got == golden["cfg2_eddsa_poseidon"]
+    assert got["verifies"] and got["wrong_input_rejected"]
+    # cfg 1: the cheap half (front end only; its full chain runs in the generator)
+    import hashlib
+    from oracle import codec
+    gates, inp, aux, *_ = gg.build_case("cfg1_poseidon_merkle")
+    g1 = golden["cfg1_poseidon_merkle"]
+    assert hashlib.sha256(b"".join(codec.gate_borsh(g) for g in gates)).hexdigest() == g1["gates_sha256"]
+    assert hex(inp[1]) == g1["public_input"] and len(aux) == g1["n_aux"]
