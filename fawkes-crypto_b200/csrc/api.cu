@@ -87,6 +87,12 @@ static void pk_release(ProvingKey* pk) {
     if (c) {
       cudaStreamDestroy(c->stream);
       for (int i = 0; i < 3; i++) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
+      if (c->stage) {
+        cudaFreeHost(c->stage);
+        for (auto& s : c->copy_stream) cudaStreamDestroy(s);
+        for (auto& e : c->stage_ev) cudaEventDestroy(e);
+        for (auto& e : c->copy_done) cudaEventDestroy(e);
+      }
       delete c;
     }
   } else if (pk->host_tables) {
@@ -161,13 +167,22 @@ static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circ
   cudaStream_t st = ctx->stream;
 #define PK_TRY(x) do { int _r = (x); if (_r) { pk_release(pk); return _r; } } while (0)
 #define PK_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); pk_release(pk); return FB_ERR_CUDA; } } while (0)
-  // vk points on host
-  if (host_decode_g1(v.alpha_g1, pk->alpha_g1) || host_decode_g1(v.beta_g1, pk->beta_g1) ||
-      host_decode_g1(v.delta_g1, pk->delta_g1) || host_decode_g2(v.beta_g2, pk->beta_g2) ||
-      host_decode_g2(v.delta_g2, pk->delta_g2)) {
-    pk_release(pk);
-    set_error("invalid verifying-key point");
-    return FB_ERR_FORMAT;
+  // vk points on host: always checked, as bellman's VerifyingKey::read does; ic points may not be at infinity
+  {
+    struct { const char* name; int rc; } vkp[5] = {
+        {"alpha_g1", host_decode_g1(v.alpha_g1, pk->alpha_g1)}, {"beta_g1", host_decode_g1(v.beta_g1, pk->beta_g1)},
+        {"delta_g1", host_decode_g1(v.delta_g1, pk->delta_g1)}, {"beta_g2", host_decode_g2(v.beta_g2, pk->beta_g2)},
+        {"delta_g2", host_decode_g2(v.delta_g2, pk->delta_g2)}};
+    G2Affine gamma;
+    int grc = host_decode_g2(v.gamma_g2, gamma);
+    for (auto& e : vkp)
+      if (e.rc) { pk_release(pk); set_error("invalid verifying-key point %s (%s)", e.name, point_error(e.rc)); return FB_ERR_FORMAT; }
+    if (grc) { pk_release(pk); set_error("invalid verifying-key point gamma_g2 (%s)", point_error(grc)); return FB_ERR_FORMAT; }
+    for (uint32_t i = 0; i < v.n_ic; i++) {
+      G1Affine icp;
+      const int irc = host_decode_g1(v.ic + 64 * (size_t)i, icp, FB_LOAD_NO_INFINITY);
+      if (irc) { pk_release(pk); set_error("invalid verifying-key point ic[%u] (%s)", i, point_error(irc)); return FB_ERR_FORMAT; }
+    }
   }
   // structural density (bellman DensityTracker: a variable counts when it appears)
   std::vector<uint8_t> a_d(pk->n_in + pk->n_aux, 0), b_d(pk->n_in + pk->n_aux, 0);
@@ -460,7 +475,7 @@ static void* build_host_tables(const ProvingKey* pk) {
 int g_msm_tables = -1;
 int g_msm_batch_affine = 0;
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
-static int g_prove_graph = -1; // CUDA-graph replay for small keys: -1 = on unless FB_PROVE_GRAPH=0, 0 off, 1 on
+static std::atomic<int> g_prove_graph{-1}; // CUDA-graph replay for small keys: -1 = on unless FB_PROVE_GRAPH=0, 0 off, 1 on
 bool kstat_enabled();
 
 // Result slots: five arrays of MSM_VBITS bit sums (G2-sized slots), order H L A B1 B2.
@@ -567,8 +582,11 @@ static int prove_graph(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_
       if (ok) ok = cudaGraphInstantiate(&pk->graph_exec, g, 0) == cudaSuccess;
       if (g) cudaGraphDestroy(g);
     }
+    // kernels enqueued between the two reads by THIS thread were captured, not run: take them off again (a
+    // subtraction, so launches counted meanwhile by other batch slots are kept; their capture windows may
+    // inflate graph_launches of this key slightly when keys are captured concurrently -- instrumentation only)
     pk->graph_launches = g_launches.load() - l0;
-    g_launches.store(l0);  // captured, not run
+    g_launches.fetch_sub(pk->graph_launches, std::memory_order_relaxed);
     if (!ok) {
       cudaGetLastError();
       pk->graph_exec = nullptr;
@@ -602,19 +620,84 @@ static int prove_graph(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_
   return FB_OK;
 }
 
+// Host -> device copy of a witness range on stream `st`.  The reference hands over `Vec<Num<Fr>>` (cs.rs:99-102):
+// PAGEABLE memory, which cudaMemcpyAsync moves through the driver's single staging buffer at a fraction of the
+// PCIe rate.  Large pageable ranges are therefore staged here: four host threads memcpy 8 MiB chunks into a ring
+// of pinned slots (two per thread) and queue one asynchronous DMA per chunk on their own copy streams, so the
+// page-touching memcpys of one chunk overlap the DMA of the others; `st` then waits for the four streams.
+// Pinned / registered memory (cudaHostAlloc, cudaHostRegister) and small ranges take the direct path.
+static constexpr size_t kStageChunk = 8u << 20;
+static constexpr int kStageThreads = 4, kStageSlots = 8;
+static int upload_host(Ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return FB_OK;
+  bool pageable = false;
+  if (bytes >= (4u << 20) && !getenv("FB_NO_STAGED_UPLOAD")) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+  }
+  if (!pageable) {
+    FB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return FB_OK;
+  }
+  if (!ctx->stage) {
+    FB_CUDA(cudaMallocHost(&ctx->stage, kStageChunk * kStageSlots));
+    for (auto& s : ctx->copy_stream) FB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : ctx->stage_ev) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ctx->copy_done) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // the copy streams must not run ahead of work already queued on st that still reads the destination
+  cudaEvent_t start = ctx->copy_done[0];
+  FB_CUDA(cudaEventRecord(start, st));
+  const size_t nchunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::atomic<int> err{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < kStageThreads; t++) {
+    th.emplace_back([&, t] {
+      cudaSetDevice(ctx->device);
+      cudaStream_t cs = ctx->copy_stream[t];
+      if (cudaStreamWaitEvent(cs, start, 0) != cudaSuccess) err = 1;
+      bool used[2] = {false, false};
+      int k = 0;
+      for (size_t c = t; c < nchunks && !err; c += kStageThreads, k ^= 1) {
+        const int slot = t * 2 + k;
+        uint8_t* sb = reinterpret_cast<uint8_t*>(ctx->stage) + (size_t)slot * kStageChunk;
+        if (used[k] && cudaEventSynchronize(ctx->stage_ev[slot]) != cudaSuccess) err = 1;
+        const size_t off = c * kStageChunk, len = std::min(kStageChunk, bytes - off);
+        memcpy(sb, reinterpret_cast<const uint8_t*>(src) + off, len);
+        if (cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + off, sb, len, cudaMemcpyHostToDevice, cs) != cudaSuccess) err = 1;
+        if (cudaEventRecord(ctx->stage_ev[slot], cs) != cudaSuccess) err = 1;
+        used[k] = true;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  if (err) { set_error("staged witness upload failed: %s", cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
+  for (int t = 0; t < kStageThreads; t++) {
+    FB_CUDA(cudaEventRecord(ctx->copy_done[t], ctx->copy_stream[t]));
+    FB_CUDA(cudaStreamWaitEvent(st, ctx->copy_done[t], 0));
+  }
+  // the ring is reused by the next call: its last DMAs must have left the slots before this returns to a caller
+  // that may immediately upload again -- stage_ev are synchronised on reuse above, and across calls here
+  for (int t = 0; t < kStageThreads; t++) FB_CUDA(cudaStreamSynchronize(ctx->copy_stream[t]));
+  return FB_OK;
+}
+
 static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t n_in,
                       const uint64_t* aux, uint32_t n_aux, const void* dev_w, const uint64_t* r,
                       const uint64_t* s, uint8_t* proof_raw, uint8_t* partial, uint64_t* h_out) {
   if (!ctx || !pk) { set_error("fb_prove: null handle"); return FB_ERR_ARG; }
+  if (ctx != pk->ctx) {  // the key's arrays, streams and events live on the context it was loaded on
+    set_error("fb_prove: the key was loaded on a different fb_ctx");
+    return FB_ERR_ARG;
+  }
   if (!dev_w && (n_in != pk->n_in || n_aux != pk->n_aux)) {
     set_error("witness has n_in=%u n_aux=%u, key expects %u / %u", n_in, n_aux, pk->n_in, pk->n_aux);
     return FB_ERR_ARG;
   }
-  if (g_prove_graph < 0) {
-    const char* e = getenv("FB_PROVE_GRAPH");
-    g_prove_graph = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  if (g_prove_graph && !dev_w && !partial && !h_out && !g_serial && !kstat_enabled() && pk->nshards == 1 &&
+  static const int graph_env = [] { const char* e = getenv("FB_PROVE_GRAPH"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  const int use_graph = g_prove_graph.load(std::memory_order_relaxed) < 0 ? graph_env : g_prove_graph.load(std::memory_order_relaxed);
+  if (use_graph && !dev_w && !partial && !h_out && !g_serial && !kstat_enabled() && pk->nshards == 1 &&
       !pk->dist_g && pk->m <= (1ull << 16) && !pk->graph_failed) {
     if (!g_timing.init) {
       for (auto& e : g_timing.ev) cudaEventCreate(&e);
@@ -644,14 +727,15 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
       const bool in_inputs = pos < n_in;
       const uint64_t seg_end = in_inputs ? std::min<uint64_t>(hi, n_in) : hi;
       const uint64_t* src = in_inputs ? inputs + 4 * pos : aux + 4 * (pos - n_in);
-      FB_CUDA(cudaMemcpyAsync(pk->w + pos, src, (seg_end - pos) * sizeof(Fr), cudaMemcpyHostToDevice, st));
+      { int urc = upload_host(ctx, pk->w + pos, src, (seg_end - pos) * sizeof(Fr), st); if (urc) return urc; }
       pos = seg_end;
     }
     int grc = dist_all_gather_inplace(ctx, pk->w, chunk * sizeof(Fr), st);
     if (grc) return grc;
   } else {
-    FB_CUDA(cudaMemcpyAsync(pk->w, inputs, (size_t)n_in * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    FB_CUDA(cudaMemcpyAsync(pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    int urc = upload_host(ctx, pk->w, inputs, (size_t)n_in * sizeof(Fr), st);
+    if (!urc) urc = upload_host(ctx, pk->w + n_in, aux, (size_t)n_aux * sizeof(Fr), st);
+    if (urc) return urc;
   }
   auto tl0 = std::chrono::steady_clock::now();
   int rc = prove_launch(pk, h_out);
@@ -769,6 +853,13 @@ void fb_shutdown(fb_ctx* ctx) {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return;
   cudaSetDevice(c->device);
+  dist_destroy(c);  // NCCL communicator and the combine buffers, if fb_dist_init was called
+  if (c->stage) {
+    cudaFreeHost(c->stage);
+    for (auto& s : c->copy_stream) cudaStreamDestroy(s);
+    for (auto& e : c->stage_ev) cudaEventDestroy(e);
+    for (auto& e : c->copy_done) cudaEventDestroy(e);
+  }
   cudaStreamDestroy(c->stream);
   for (int i = 0; i < 3; i++) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
   delete c;
@@ -793,10 +884,20 @@ int fb_circuit_from_raw_gates(const uint8_t* gates, size_t len, uint32_t num_gat
   return FB_OK;
 }
 
+// Most bytes a gate stream announcing `num_gates` gates over n_in + n_aux variables can hold: three LCs per
+// gate, each a u32 count and at most one 37-byte term per variable (LCs are kept canonical, lc.rs:89-118);
+// capped by an absolute limit (FB_MAX_GATE_BYTES, default 32 GiB: configs[4] is ~9 GB).
+static size_t gate_stream_cap(uint32_t num_gates, uint32_t n_in, uint32_t n_aux) {
+  size_t abs_cap = (size_t)32 << 30;
+  if (const char* e = getenv("FB_MAX_GATE_BYTES")) abs_cap = (size_t)strtoull(e, nullptr, 10);
+  const long double theo = (long double)num_gates * 3.0L * (4.0L + 37.0L * ((long double)n_in + n_aux));
+  return theo < (long double)abs_cap ? (size_t)theo + 1 : abs_cap;
+}
+
 int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_gates, uint32_t n_in,
                           uint32_t n_aux, fb_circuit** out) {
   std::vector<uint8_t> raw;
-  int rc = brotli_decode(gates_brotli, len, raw);
+  int rc = brotli_decode(gates_brotli, len, raw, gate_stream_cap(num_gates, n_in, n_aux));
   if (rc) return rc;
   return fb_circuit_from_raw_gates(raw.data(), raw.size(), num_gates, n_in, n_aux, out);
 }
@@ -822,7 +923,7 @@ int fb_circuit_from_gates_gpu(fb_ctx* ctx, const uint8_t* gates_brotli, size_t l
                               uint32_t n_aux, fb_circuit** out, float* times_ms) {
   std::vector<uint8_t> raw;
   auto t0 = std::chrono::steady_clock::now();
-  int rc = brotli_decode(gates_brotli, len, raw);
+  int rc = brotli_decode(gates_brotli, len, raw, gate_stream_cap(num_gates, n_in, n_aux));
   if (rc) return rc;
   if (times_ms) times_ms[4] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return fb_circuit_from_raw_gates_gpu(ctx, raw.data(), raw.size(), num_gates, n_in, n_aux, out, times_ms);
@@ -899,12 +1000,59 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
   return FB_OK;
 }
 
+// Sharded key on a distributed context (fb_dist_init + fb_pk_load_shard(rank, world)): a COLLECTIVE prove.  Every
+// rank calls with the same witness, r and s; each computes the partial sums of its base shard, the 640-byte
+// partials are all-gathered over the library's NCCL communicator (NVLink) and every rank assembles and returns
+// the same proof.
+static int prove_collective(Ctx* ctx, ProvingKey* p, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
+                            uint32_t n_aux, const void* dev_w, const uint64_t r[4], const uint64_t s[4],
+                            uint8_t proof_raw[256]) {
+  if (!ctx->exchange || ctx->world != p->nshards || ctx->rank != p->shard) {
+    set_error("fb_prove on a sharded key needs a context initialised with fb_dist_init(rank = shard, world = nshards); "
+              "use fb_prove_partial / fb_prove_finish with your own transport otherwise");
+    return FB_ERR_ARG;
+  }
+  uint8_t mine[640];
+  int rc = prove_impl(ctx, p, inputs, n_in, aux, n_aux, dev_w, nullptr, nullptr, nullptr, mine, nullptr);
+  if (rc) return rc;
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<uint8_t> all((size_t)ctx->world * 640);
+  rc = dist_gather_partials(ctx, mine, all.data(), ctx->stream);
+  if (rc) return rc;
+  H1 sum[4] = {H1::inf(), H1::inf(), H1::inf(), H1::inf()};
+  H2 sum2 = H2::inf();
+  for (int i = 0; i < ctx->world; i++) {
+    const uint8_t* q = all.data() + (size_t)i * 640;
+    for (int j = 0; j < 4; j++) {
+      G1Affine a;
+      memcpy(&a, q + 128 * j, 64);
+      sum[j] = add(sum[j], h1_from(a));
+    }
+    G2Affine b;
+    memcpy(&b, q + 512, 128);
+    sum2 = add(sum2, h2_from(b));
+  }
+  FixedTerms ft;
+  VkPoints vk{p->alpha_g1, p->beta_g1, p->delta_g1, p->beta_g2, p->delta_g2};
+  rc = fixed_terms(&vk, reinterpret_cast<const KeyTables*>(p->host_tables), r, s, ft);
+  if (rc) return rc;
+  finish_proof(ft, sum[0], sum[1], sum[2], sum[3], sum2, nullptr, nullptr, proof_raw);
+  const double combine_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  g_timing.ms[4] += (float)combine_ms;
+  g_timing.ms[5] += (float)combine_ms;
+  return FB_OK;
+}
+
 int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
              uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
              uint64_t* h_out) {
   if (!inputs || (!aux && n_aux) || !r || !s || !proof_raw) { set_error("fb_prove: null buffer"); return FB_ERR_ARG; }
   ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
-  if (p && p->nshards != 1) { set_error("fb_prove on a sharded key: use fb_prove_partial"); return FB_ERR_ARG; }
+  if (p && p->nshards != 1) {
+    if (h_out) { set_error("h_out is not available on a sharded key"); return FB_ERR_ARG; }
+    if (!ctx) { set_error("fb_prove: null handle"); return FB_ERR_ARG; }
+    return prove_collective(reinterpret_cast<Ctx*>(ctx), p, inputs, n_in, aux, n_aux, nullptr, r, s, proof_raw);
+  }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), p, inputs, n_in, aux, n_aux, nullptr, r, s,
                     proof_raw, nullptr, h_out);
 }
@@ -1021,6 +1169,7 @@ struct ProveStream {
   std::set<uint64_t> outstanding;  // submitted and not collected yet
   uint64_t next_ticket = 1;
   size_t in_flight = 0, depth = 1;
+  int waiters = 0;  // threads inside fb_stream_wait
   bool closing = false;
   std::vector<std::thread> workers;
   // one pinned witness buffer per proof that can be queued or running: submit is a plain memcpy (no page
@@ -1132,11 +1281,15 @@ int fb_stream_wait(fb_stream* st_, uint64_t ticket, uint8_t proof_raw[256]) {
   if (!st || !proof_raw) { set_error("fb_stream_wait: bad argument"); return FB_ERR_ARG; }
   std::unique_lock<std::mutex> lk(st->mu);
   if (!st->outstanding.count(ticket)) { set_error("fb_stream_wait: unknown or already collected ticket"); return FB_ERR_ARG; }
+  st->waiters++;
   st->cv_done.wait(lk, [&] { return st->done.count(ticket) != 0; });
+  st->waiters--;
   st->outstanding.erase(ticket);
   ProveStream::Result res = std::move(st->done[ticket]);
   st->done.erase(ticket);
+  const bool closing = st->closing;
   lk.unlock();
+  if (closing) st->cv_done.notify_all();
   if (res.rc) { set_error("%s", res.err.c_str()); return res.rc; }
   memcpy(proof_raw, res.proof, 256);
   return FB_OK;
@@ -1148,11 +1301,25 @@ void fb_stream_close(fb_stream* st_) {
   {
     std::lock_guard<std::mutex> lk(st->mu);
     st->closing = true;
+    // proofs not started yet are dropped: publish an error result for each, so a thread blocked in
+    // fb_stream_wait on one of them returns instead of waiting for ever
+    for (const ProveStream::Job& job : st->queue) {
+      ProveStream::Result res;
+      res.rc = FB_ERR_ARG;
+      res.err = "fb_stream_close: the stream was closed before this proof started";
+      st->done.emplace(job.ticket, std::move(res));
+      st->free_bufs.push_back(job.buf);
+    }
     st->in_flight -= st->queue.size();
-    st->queue.clear();  // proofs not started yet are dropped
+    st->queue.clear();
   }
   st->cv_job.notify_all();
+  st->cv_done.notify_all();
   for (auto& t : st->workers) t.join();
+  {  // let waiters that were woken up leave fb_stream_wait before the object goes away
+    std::unique_lock<std::mutex> lk(st->mu);
+    st->cv_done.wait(lk, [&] { return st->waiters == 0; });
+  }
   for (uint64_t* b : st->bufs) cudaFreeHost(b);
   delete st;
 }
@@ -1161,7 +1328,10 @@ int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[
                     const uint64_t s[4], uint8_t proof_raw[256]) {
   if (!dev_w || !r || !s || !proof_raw) { set_error("fb_prove_device: null buffer"); return FB_ERR_ARG; }
   ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
-  if (p && p->nshards != 1) { set_error("fb_prove_device on a sharded key"); return FB_ERR_ARG; }
+  if (p && p->nshards != 1) {  // collective, see fb_prove: every rank passes its own device copy of the witness
+    if (!ctx) { set_error("fb_prove_device: null handle"); return FB_ERR_ARG; }
+    return prove_collective(reinterpret_cast<Ctx*>(ctx), p, nullptr, 0, nullptr, 0, dev_w, r, s, proof_raw);
+  }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), p, nullptr, 0, nullptr, 0, dev_w, r, s, proof_raw,
                     nullptr, nullptr);
 }
@@ -1219,7 +1389,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
 uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
-void fb_set_prove_graph(int on) { fb::g_prove_graph = on ? 1 : 0; }
+void fb_set_prove_graph(int on) { fb::g_prove_graph.store(on ? 1 : 0); }
 void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 2) ? 0 : on; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }

@@ -34,9 +34,8 @@ struct NcclApi {
 };
 static NcclApi& nccl() {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (lib) {
@@ -51,13 +50,16 @@ static NcclApi& nccl() {
       api.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
       api.ok = api.GetUniqueId && api.CommInitRank && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
     }
-  }
+  });
   return api;
 }
 
 struct NcclExchange : NttExchange {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // combine step of a sharded prove: world x 640-byte partial sums (device + pinned host mirror)
+  uint8_t* gather_dev = nullptr;
+  uint8_t* gather_host = nullptr;
   int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count, cudaStream_t st) override {
     NcclApi& n = nccl();
     int rc = n.GroupStart();
@@ -88,6 +90,43 @@ int dist_all_gather_inplace(Ctx* ctx, void* buf, size_t chunk_bytes, cudaStream_
   if (rc) { set_error("ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(rc) : "?"); return FB_ERR_CUDA; }
   count_launch(1);
   return 0;
+}
+
+// Combine step of a sharded prove (north_star (4): "partial sums combined over NVLink"): every rank contributes
+// its five affine partial sums (640 B, the fb_prove_partial layout) and receives everybody's, in rank order.
+// One ncclAllGather over the library's communicator on the prove stream; `all` is host memory, world x 640 B.
+int dist_gather_partials(Ctx* ctx, const uint8_t* mine, uint8_t* all, cudaStream_t st) {
+  NcclExchange* x = reinterpret_cast<NcclExchange*>(ctx->exchange);
+  NcclApi& n = nccl();
+  if (!x || !n.AllGather) { set_error("NCCL all-gather unavailable"); return FB_ERR_CUDA; }
+  const size_t total = (size_t)x->world * 640;
+  if (!x->gather_dev) {
+    FB_CUDA(cudaMalloc(&x->gather_dev, total));
+    FB_CUDA(cudaMallocHost(&x->gather_host, total));
+  }
+  memcpy(x->gather_host + (size_t)x->rank * 640, mine, 640);
+  FB_CUDA(cudaMemcpyAsync(x->gather_dev + (size_t)x->rank * 640, x->gather_host + (size_t)x->rank * 640, 640,
+                          cudaMemcpyHostToDevice, st));
+  int rc = n.AllGather(x->gather_dev + (size_t)x->rank * 640, x->gather_dev, 640, kNcclUint8, x->comm, st);
+  if (rc) { set_error("ncclAllGather: %s", n.GetErrorString ? n.GetErrorString(rc) : "?"); return FB_ERR_CUDA; }
+  count_launch(1);
+  FB_CUDA(cudaMemcpyAsync(x->gather_host, x->gather_dev, total, cudaMemcpyDeviceToHost, st));
+  FB_CUDA(cudaStreamSynchronize(st));
+  memcpy(all, x->gather_host, total);
+  return FB_OK;
+}
+
+void dist_destroy(Ctx* ctx) {
+  NcclExchange* x = reinterpret_cast<NcclExchange*>(ctx->exchange);
+  if (!x) return;
+  if (x->gather_dev) cudaFree(x->gather_dev);
+  if (x->gather_host) cudaFreeHost(x->gather_host);
+  NcclApi& n = nccl();
+  if (x->comm && n.CommDestroy) n.CommDestroy(x->comm);
+  delete x;
+  ctx->exchange = nullptr;
+  ctx->world = 1;
+  ctx->rank = 0;
 }
 
 // ---- single-process stand-in used by the one-GPU test: G host threads, one per virtual rank ----
@@ -153,6 +192,7 @@ int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) {
   x->world = world;
   int rc = n.CommInitRank(&x->comm, world, u, rank);
   if (rc) { set_error("ncclCommInitRank: %s", n.GetErrorString(rc)); delete x; return FB_ERR_CUDA; }
+  if (ctx->exchange) dist_destroy(ctx);
   ctx->exchange = x;
   ctx->rank = rank;
   ctx->world = world;

@@ -65,6 +65,11 @@ struct Ctx {
   // multi-GPU (fb_dist_init): rank / world of this process and the NTT exchange transport
   int rank = 0, world = 1;
   void* exchange = nullptr;  // NttExchange*
+  // staged upload of pageable witness buffers (api.cu: upload_host): pinned ring + copy streams, made on first use
+  void* stage = nullptr;
+  cudaStream_t copy_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t copy_done[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ProvingKey {
@@ -131,17 +136,19 @@ int parse_params(const uint8_t* b, size_t len, ParamsView& v);  // api.cu
 
 // pk.cu
 int parse_gates_to_csr(const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out);
-int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out);
+int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out, size_t max_out);
 int upload_csr(const HostCsr& h, DevCsr& d, cudaStream_t st);
 // ingest.cu: the same CSR with the per-term work (parse, range checks, Montgomery form, dictionary) on the GPU
 struct Ctx;
 int parse_gates_device(Ctx* ctx, const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out,
                        float* times_ms);
 void free_csr(DevCsr& d);
-int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, bool checked, cudaStream_t st);
-int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, bool checked, cudaStream_t st);
-int host_decode_g1(const uint8_t* be, G1Affine& out);
-int host_decode_g2(const uint8_t* be, G2Affine& out);
+// flags: FB_LOAD_CHECKED | FB_LOAD_NO_INFINITY (include/fawkes_b200.h)
+int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, int flags, cudaStream_t st);
+int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, int flags, cudaStream_t st);
+int host_decode_g1(const uint8_t* be, G1Affine& out, int extra_flags = 0);  // always checked; 0 or a point_error code
+int host_decode_g2(const uint8_t* be, G2Affine& out, int extra_flags = 0);
+const char* point_error(int code);
 void host_encode_g1(const G1Affine& p, uint8_t* be);
 void host_encode_g2(const G2Affine& p, uint8_t* be);
 
@@ -149,6 +156,8 @@ void host_encode_g2(const G2Affine& p, uint8_t* be);
 struct NttExchange;
 NttExchange* dist_exchange(Ctx* ctx);
 int dist_all_gather_inplace(Ctx* ctx, void* buf, size_t chunk_bytes, cudaStream_t st);
+int dist_gather_partials(Ctx* ctx, const uint8_t* mine, uint8_t* all, cudaStream_t st);  // 640 B per rank
+void dist_destroy(Ctx* ctx);  // communicator + buffers (fb_shutdown)
 
 // prove.cu
 int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,

@@ -12,6 +12,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <mutex>
 #include <unordered_map>
 
 #include "internal.h"
@@ -32,7 +33,8 @@ const char* last_error_cstr() { return g_err.c_str(); }
 std::atomic<unsigned long long> g_launches{0};
 namespace {
 struct KStat {
-  bool enabled = false;
+  std::atomic<bool> enabled{false};
+  std::mutex mu;  // batch slots and stream workers launch MSMs concurrently
   std::vector<cudaEvent_t> pool;
   struct Rec { int kind; cudaEvent_t a, b; };
   std::vector<Rec> open_recs, recs;
@@ -48,12 +50,14 @@ struct KStat {
 }  // namespace
 void kstat_begin(int kind, cudaStream_t st) {
   if (!g_ks.enabled) return;
+  std::lock_guard<std::mutex> lk(g_ks.mu);
   KStat::Rec r{kind, g_ks.get(), g_ks.get()};
   cudaEventRecord(r.a, st);
   g_ks.open_recs.push_back(r);
 }
 void kstat_end(int kind, cudaStream_t st) {
   if (!g_ks.enabled) return;
+  std::lock_guard<std::mutex> lk(g_ks.mu);
   for (size_t i = g_ks.open_recs.size(); i-- > 0;) {
     if (g_ks.open_recs[i].kind == kind) {
       cudaEventRecord(g_ks.open_recs[i].b, st);
@@ -66,12 +70,14 @@ void kstat_end(int kind, cudaStream_t st) {
 void kstat_enable(bool on) { g_ks.enabled = on; }
 bool kstat_enabled() { return g_ks.enabled; }
 void kstat_reset() {
+  std::lock_guard<std::mutex> lk(g_ks.mu);
   for (auto& r : g_ks.recs) { g_ks.pool.push_back(r.a); g_ks.pool.push_back(r.b); }
   g_ks.recs.clear();
   for (int i = 0; i < KSTAT_KINDS; i++) { g_ks.count[i] = 0; g_ks.ms[i] = 0; }
 }
 void kstat_collect(int kind, unsigned long long* launches, double* ms) {
   cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_ks.mu);
   for (auto& r : g_ks.recs) {
     float t = 0;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { g_ks.count[r.kind]++; g_ks.ms[r.kind] += t; }
@@ -90,44 +96,67 @@ typedef BrotliDecoderState* (*fn_create)(void*, void*, void*);
 typedef int (*fn_stream)(BrotliDecoderState*, size_t*, const uint8_t**, size_t*, uint8_t**, size_t*);
 typedef void (*fn_destroy)(BrotliDecoderState*);
 
-int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out) {
-  static void* lib = nullptr;
-  static fn_create create;
-  static fn_stream stream;
-  static fn_destroy destroy;
-  if (!lib) {
-    lib = dlopen("libbrotlidec.so.1", RTLD_NOW);
-    if (!lib) {
-      set_error("cannot load libbrotlidec.so.1: %s", dlerror());
-      return FB_ERR_FORMAT;
-    }
-    create = (fn_create)dlsym(lib, "BrotliDecoderCreateInstance");
-    stream = (fn_stream)dlsym(lib, "BrotliDecoderDecompressStream");
-    destroy = (fn_destroy)dlsym(lib, "BrotliDecoderDestroyInstance");
-    if (!create || !stream || !destroy) {
-      set_error("libbrotlidec.so.1 lacks the streaming API");
-      return FB_ERR_FORMAT;
-    }
-  }
-  BrotliDecoderState* st = create(nullptr, nullptr, nullptr);
+namespace {
+struct BrotliApi {
+  void* lib = nullptr;
+  fn_create create = nullptr;
+  fn_stream stream = nullptr;
+  fn_destroy destroy = nullptr;
+  std::string err;
+};
+const BrotliApi& brotli_api() {
+  static BrotliApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    api.lib = dlopen("libbrotlidec.so.1", RTLD_NOW);
+    if (!api.lib) { api.err = std::string("cannot load libbrotlidec.so.1: ") + dlerror(); return; }
+    api.create = (fn_create)dlsym(api.lib, "BrotliDecoderCreateInstance");
+    api.stream = (fn_stream)dlsym(api.lib, "BrotliDecoderDecompressStream");
+    api.destroy = (fn_destroy)dlsym(api.lib, "BrotliDecoderDestroyInstance");
+    if (!api.create || !api.stream || !api.destroy) api.err = "libbrotlidec.so.1 lacks the streaming API";
+  });
+  return api;
+}
+}  // namespace
+
+// max_out: the most the stream may legitimately expand to (callers derive it from num_gates and the
+// variable counts); a stream that wants more is rejected instead of growing without bound.
+int brotli_decode(const uint8_t* in, size_t len, std::vector<uint8_t>& out, size_t max_out) {
+  const BrotliApi& api = brotli_api();
+  if (!api.err.empty()) { set_error("%s", api.err.c_str()); return FB_ERR_FORMAT; }
+  BrotliDecoderState* st = api.create(nullptr, nullptr, nullptr);
+  if (!st) { set_error("BrotliDecoderCreateInstance failed"); return FB_ERR_FORMAT; }
   out.clear();
-  out.resize(std::max<size_t>(len * 4, 1 << 16));
+  out.resize(std::min<size_t>(std::max<size_t>(len * 4, 1 << 16), std::max<size_t>(max_out, 1)));
   size_t avail_in = len, produced = 0;
   const uint8_t* next_in = in;
+  int rc = FB_OK;
   for (;;) {
     size_t avail_out = out.size() - produced;
     uint8_t* next_out = out.data() + produced;
-    int r = stream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
+    const int r = api.stream(st, &avail_in, &next_in, &avail_out, &next_out, nullptr);
     produced = out.size() - avail_out;
-    if (r == 1) break;                       // BROTLI_DECODER_RESULT_SUCCESS
-    if (r == 3) { out.resize(out.size() * 2); continue; }  // NEEDS_MORE_OUTPUT
-    // error or truncated input: the reference's Decompressor would surface a read
-    // error and GateStreamedIterator stops (cs.rs:215-223); keep what was produced.
+    if (r == 1) break;  // BROTLI_DECODER_RESULT_SUCCESS
+    if (r == 3) {       // NEEDS_MORE_OUTPUT
+      if (out.size() >= max_out) {
+        set_error("gate stream expands beyond %zu bytes (more than the announced gate count can hold)", max_out);
+        rc = FB_ERR_FORMAT;
+        break;
+      }
+      out.resize(std::min<size_t>(out.size() * 2, max_out));
+      continue;
+    }
+    // r == 0 (corrupt stream) or r == 2 (input ends inside the stream).  The reference's Decompressor surfaces
+    // an io error there and the prover would run on a truncated circuit; at a key-load boundary that is an error.
+    set_error(r == 2 ? "gate stream is truncated (brotli needs more input after %zu bytes)"
+                     : "gate stream is not valid brotli (decoder error after %zu output bytes)",
+              r == 2 ? len : produced);
+    rc = FB_ERR_FORMAT;
     break;
   }
-  destroy(st);
-  out.resize(produced);
-  return FB_OK;
+  api.destroy(st);
+  out.resize(rc == FB_OK ? produced : 0);
+  return rc;
 }
 
 // ------------------------------------------------------------- gate parse ---
@@ -252,22 +281,56 @@ FB_HD void limbs_to_be(const uint32_t* v, uint8_t* be) {
   }
 }
 
-// returns 0 ok, 1 = coordinate >= p, 2 = not on curve, 3 = bad flag
-FB_HD int decode_g1(const uint8_t* be, G1Affine& out, bool checked) {
-  if (be[0] & 0x40) { out = G1Affine::inf(); return 0; }
+// Decoder of pairing_ce's `Uncompressed` encoding as bellman's Parameters::read drives it (bellman_ce 0.3.5
+// groth16/mod.rs `read_g1/read_g2` closures, restated -- the crate is not vendored):
+//   unchecked (`into_affine_unchecked`): bit 7 (compression) must be clear; bit 6 = infinity, and then every other
+//     bit of the encoding must be zero; coordinates must be < p;
+//   checked   (`into_affine`): additionally on the curve and in the r-torsion subgroup (G1 has cofactor 1, so the
+//     subgroup test only costs anything for G2: [r]P == O);
+//   disallow_points_at_infinity: the point at infinity is an error.
+// flags: FB_LOAD_CHECKED | FB_LOAD_NO_INFINITY.
+// returns 0 ok, 1 = coordinate >= p, 2 = not on curve, 3 = bad flag, 4 = dirty infinity encoding,
+// 5 = not in the r-torsion subgroup, 6 = point at infinity where none is allowed
+template <int SZ>
+FB_HD bool inf_encoding_clean(const uint8_t* be) {
+  if (be[0] != 0x40) return false;
+  for (int i = 1; i < SZ; i++)
+    if (be[i]) return false;
+  return true;
+}
+template <class F>
+FB_HD_COLD bool in_r_torsion(const Affine<F>& p) {
+  uint32_t r[8];
+  for (int i = 0; i < 8; i++) r[i] = FrCfg::mod(i);
+  return scalar_mul(XYZZ<F>::from_affine(p), r).is_inf();
+}
+FB_HD int decode_g1(const uint8_t* be, G1Affine& out, int flags) {
   if (be[0] & 0x80) return 3;
+  if (be[0] & 0x40) {
+    if (!inf_encoding_clean<64>(be)) return 4;
+    if (flags & FB_LOAD_NO_INFINITY) return 6;
+    out = G1Affine::inf();
+    return 0;
+  }
   Fq x, y;
   be_to_limbs(be, x.v);
   be_to_limbs(be + 32, y.v);
   if (geq_mod<FqCfg>(x.v) || geq_mod<FqCfg>(y.v)) return 1;
   out.x = to_mont(x);
   out.y = to_mont(y);
-  if (checked && !on_curve(out, g1_b())) return 2;
+  // (0, 0) is the in-memory form of infinity (group.rs:55) and is not on the curve: never a valid encoding
+  if ((flags & FB_LOAD_CHECKED) && !on_curve(out, g1_b())) return 2;
+  if (out.is_inf()) return 2;
   return 0;
 }
-FB_HD int decode_g2(const uint8_t* be, G2Affine& out, bool checked) {
-  if (be[0] & 0x40) { out = G2Affine::inf(); return 0; }
+FB_HD int decode_g2(const uint8_t* be, G2Affine& out, int flags) {
   if (be[0] & 0x80) return 3;
+  if (be[0] & 0x40) {
+    if (!inf_encoding_clean<128>(be)) return 4;
+    if (flags & FB_LOAD_NO_INFINITY) return 6;
+    out = G2Affine::inf();
+    return 0;
+  }
   Fq c[4];
   for (int i = 0; i < 4; i++) {
     be_to_limbs(be + 32 * i, c[i].v);
@@ -276,70 +339,93 @@ FB_HD int decode_g2(const uint8_t* be, G2Affine& out, bool checked) {
   }
   out.x = {c[1], c[0]};  // bytes are x.c1 | x.c0 | y.c1 | y.c0
   out.y = {c[3], c[2]};
-  if (checked && !on_curve(out, g2_b())) return 2;
+  if (out.is_inf()) return 2;
+  if (flags & FB_LOAD_CHECKED) {
+    if (!on_curve(out, g2_b())) return 2;
+    if (!in_r_torsion(out)) return 5;
+  }
   return 0;
 }
 
 __global__ void k_decode_g1(const uint8_t* __restrict__ be, uint64_t n, G1Affine* __restrict__ out,
-                            bool checked, int* __restrict__ err) {
+                            int flags, int* __restrict__ err) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
     G1Affine p;
-    int e = decode_g1(be + i * 64, p, checked);
+    int e = decode_g1(be + i * 64, p, flags);
     if (e) atomicMax(err, e);
     else out[i] = p;
   }
 }
 __global__ void k_decode_g2(const uint8_t* __restrict__ be, uint64_t n, G2Affine* __restrict__ out,
-                            bool checked, int* __restrict__ err) {
+                            int flags, int* __restrict__ err) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
     G2Affine p;
-    int e = decode_g2(be + i * 128, p, checked);
+    int e = decode_g2(be + i * 128, p, flags);
     if (e) atomicMax(err, e);
     else out[i] = p;
   }
 }
 
+static const char* point_error_name(int e) {
+  switch (e) {
+    case 1: return "coordinate not in field";
+    case 2: return "not on curve";
+    case 3: return "unexpected compression flag";
+    case 4: return "unexpected information in the encoding of the point at infinity";
+    case 5: return "not in the r-torsion subgroup";
+    case 6: return "point at infinity";
+    default: return "invalid";
+  }
+}
+
+namespace {
+struct DevBuf {  // cudaFree on every exit path
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
 template <class P, int SZ, class K>
-static int decode_points(const uint8_t* host_be, uint64_t n, P* dev_out, bool checked,
+static int decode_points(const uint8_t* host_be, uint64_t n, P* dev_out, int flags,
                          cudaStream_t st, K kernel) {
   if (n == 0) return FB_OK;
   // stage through a bounded device buffer so a 16 GiB key does not need 16 GiB of staging
   const uint64_t chunk = std::min<uint64_t>(n, 1ull << 22);
-  uint8_t* stage = nullptr;
-  int* derr = nullptr;
-  FB_CUDA(cudaMalloc(&stage, chunk * SZ));
-  FB_CUDA(cudaMalloc(&derr, 4));
+  DevBuf stage_b, derr_b;
+  FB_CUDA(cudaMalloc(&stage_b.p, chunk * SZ));
+  FB_CUDA(cudaMalloc(&derr_b.p, 4));
+  uint8_t* stage = reinterpret_cast<uint8_t*>(stage_b.p);
+  int* derr = reinterpret_cast<int*>(derr_b.p);
   FB_CUDA(cudaMemsetAsync(derr, 0, 4, st));
   for (uint64_t off = 0; off < n; off += chunk) {
     uint64_t cnt = std::min(chunk, n - off);
     FB_CUDA(cudaMemcpyAsync(stage, host_be + off * SZ, cnt * SZ, cudaMemcpyHostToDevice, st));
     unsigned blocks = (unsigned)std::min<uint64_t>((cnt + 127) / 128, 148 * 16);
-    kernel<<<blocks, 128, 0, st>>>(stage, cnt, dev_out + off, checked, derr);
+    kernel<<<blocks, 128, 0, st>>>(stage, cnt, dev_out + off, flags, derr);
     FB_CUDA(cudaStreamSynchronize(st));
   }
   int herr = 0;
   FB_CUDA(cudaMemcpyAsync(&herr, derr, 4, cudaMemcpyDeviceToHost, st));
   FB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(stage);
-  cudaFree(derr);
   if (herr) {
-    set_error("invalid point in Parameters (%s)",
-              herr == 1 ? "coordinate not in field" : herr == 2 ? "not on curve" : "bad flag bits");
+    set_error("invalid point in Parameters (%s)", point_error_name(herr));
     return FB_ERR_FORMAT;
   }
   return FB_OK;
 }
 
-int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, bool checked, cudaStream_t st) {
-  return decode_points<G1Affine, 64>(host_be, n, dev_out, checked, st, k_decode_g1);
+int decode_g1_be(const uint8_t* host_be, uint64_t n, G1Affine* dev_out, int flags, cudaStream_t st) {
+  return decode_points<G1Affine, 64>(host_be, n, dev_out, flags, st, k_decode_g1);
 }
-int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, bool checked, cudaStream_t st) {
-  return decode_points<G2Affine, 128>(host_be, n, dev_out, checked, st, k_decode_g2);
+int decode_g2_be(const uint8_t* host_be, uint64_t n, G2Affine* dev_out, int flags, cudaStream_t st) {
+  return decode_points<G2Affine, 128>(host_be, n, dev_out, flags, st, k_decode_g2);
 }
-int host_decode_g1(const uint8_t* be, G1Affine& out) { return decode_g1(be, out, true); }
-int host_decode_g2(const uint8_t* be, G2Affine& out) { return decode_g2(be, out, true); }
+// verifying-key points are always read checked (bellman VerifyingKey::read uses into_affine)
+int host_decode_g1(const uint8_t* be, G1Affine& out, int extra_flags) { return decode_g1(be, out, FB_LOAD_CHECKED | extra_flags); }
+int host_decode_g2(const uint8_t* be, G2Affine& out, int extra_flags) { return decode_g2(be, out, FB_LOAD_CHECKED | extra_flags); }
+const char* point_error(int e) { return point_error_name(e); }
 
 void host_encode_g1(const G1Affine& p, uint8_t* be) {
   memset(be, 0, 64);

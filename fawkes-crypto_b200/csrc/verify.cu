@@ -161,6 +161,34 @@ extern "C" int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t pro
     set_error("MalformedVerifyingKey: %u inputs for %u ic points", n_inputs, n_ic);
     return FB_ERR_VK;
   }
+  // The reference converts every point with `from_raw_uncompressed_le(..).unwrap()` (group.rs:53-65,87-105) and
+  // every input with `from_raw_repr(..).unwrap()` (mod.rs:105-120): limbs >= the modulus or a point off its curve
+  // panic there.  Here they are a format error, so that no second bit pattern of the same residue (x and x + r)
+  // can verify for one statement.
+  auto canonical = [](const uint8_t* p, int n_fq) {
+    for (int i = 0; i < n_fq; i++) {
+      uint32_t v[8];
+      memcpy(v, p + 32 * i, 32);
+      if (geq_mod<FqCfg>(v)) return false;
+    }
+    return true;
+  };
+  if (!canonical(vk_raw, 2 + 4 + 4 + 4) || !canonical(vk_raw + 448, 2 * (int)n_ic)) {
+    set_error("verifying key holds a coordinate that is not a reduced field element");
+    return FB_ERR_FORMAT;
+  }
+  if (!canonical(proof_raw, 8)) {
+    set_error("proof holds a coordinate that is not a reduced field element");
+    return FB_ERR_FORMAT;
+  }
+  for (uint32_t i = 0; i < n_inputs; i++) {
+    uint32_t v[8];
+    memcpy(v, inputs + 4 * (size_t)i, 32);
+    if (geq_mod<FrCfg>(v)) {
+      set_error("public input %u is not a reduced field element", i);
+      return FB_ERR_FORMAT;
+    }
+  }
   G1Affine alpha, A, C;
   G2Affine beta, gamma, delta, B;
   memcpy(&alpha, vk_raw, 64);
@@ -171,7 +199,22 @@ extern "C" int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t pro
   memcpy(&A, proof_raw, 64);
   memcpy(&B, proof_raw + 64, 128);
   memcpy(&C, proof_raw + 192, 64);
-  if (!on_curve(A, g1_b()) || !on_curve(C, g1_b()) || !on_curve(B, g2_b())) return FB_OK;  // ok = 0
+  if (!on_curve(alpha, g1_b()) || !on_curve(beta, g2_b()) || !on_curve(gamma, g2_b()) || !on_curve(delta, g2_b())) {
+    set_error("verifying-key point not on its curve");
+    return FB_ERR_FORMAT;
+  }
+  for (uint32_t i = 0; i < n_ic; i++) {
+    G1Affine p;
+    memcpy(&p, ic + 64 * (size_t)i, 64);
+    if (!on_curve(p, g1_b())) {
+      set_error("verifying-key point ic[%u] not on the curve", i);
+      return FB_ERR_FORMAT;
+    }
+  }
+  if (!on_curve(A, g1_b()) || !on_curve(C, g1_b()) || !on_curve(B, g2_b())) {
+    set_error("proof point not on its curve");
+    return FB_ERR_FORMAT;
+  }
   G1Affine ic0;
   memcpy(&ic0, ic, 64);
   G1XYZZ acc = G1XYZZ::from_affine(ic0);

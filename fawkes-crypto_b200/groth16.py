@@ -261,7 +261,9 @@ class Parameters:
         self.const_tracker = list(const_tracker)
         self._circuit = circuit
         self._pk = None
-        self._pk_ctx = None
+        self._pk_key = None     # (ctx, shard, nshards, flags) the resident key was loaded with
+        self._checked = True
+        self._disallow_inf = False
 
     # -- (de)serialisation, mod.rs:150-175 ------------------------------------
     def write(self) -> bytes:
@@ -290,7 +292,9 @@ class Parameters:
         pos += nbytes
         bits = [bool(bv[i // 8] & (0x80 >> (i % 8))) for i in range(nbits)]
         p = cls(data[pos:], num_gates, blob, bits)
-        p._checked = checked
+        # the two flags of bellman's Parameters::read are applied where the points are decoded: at key load
+        p._checked = bool(checked)
+        p._disallow_inf = bool(disallow_points_at_infinity)
         return p
 
     # -- views -----------------------------------------------------------------
@@ -324,13 +328,23 @@ class Parameters:
             self._circuit = Circuit.from_gates_blob(self.gates_blob, self.num_gates, self.n_in, self.n_aux, ctx)
         return self._circuit
 
-    def load(self, ctx: Context, checked: bool = True, shard: int = 0, nshards: int = 1):
-        """Upload the proving key to HBM (fb_pk_load_*); cached per Parameters."""
+    def load(self, ctx: Context, checked: Optional[bool] = None, shard: int = 0, nshards: int = 1):
+        """Upload the proving key to HBM (fb_pk_load_shard).  One resident key per Parameters: asking for it
+        again with another context, shard or flags is an error (unload() first) -- a key's arrays, streams and
+        events belong to the context it was loaded on."""
+        if checked is None and self._pk is not None and self._pk_key[:3] == (id(ctx), shard, nshards):
+            return self._pk     # whatever flags the resident key was validated with
+        checked = self._checked if checked is None else bool(checked)
+        flags = (nv.FB_LOAD_CHECKED if checked else 0) | (nv.FB_LOAD_NO_INFINITY if self._disallow_inf else 0)
+        key = (id(ctx), shard, nshards, flags)
+        if self._pk is not None and self._pk_key != key:
+            raise ValueError("Parameters.load: a key is already resident with another context / shard / flags; "
+                             "call unload() first")
         if self._pk is None:
             h = C.c_void_p()
             nv.check(nv.lib.fb_pk_load_shard(ctx.handle, nv.ptr(self.bellman_bytes), len(self.bellman_bytes),
-                                             self.circuit(ctx).handle, int(checked), shard, nshards, C.byref(h)))
-            self._pk, self._pk_ctx = h, ctx
+                                             self.circuit(ctx).handle, flags, shard, nshards, C.byref(h)))
+            self._pk, self._pk_key, self._pk_ctx = h, key, ctx
         return self._pk
 
     def info(self) -> dict:
@@ -347,6 +361,7 @@ class Parameters:
         if self._pk is not None:
             nv.lib.fb_pk_free(self._pk)
             self._pk = None
+            self._pk_key = None
 
     def __del__(self):
         try:
@@ -386,7 +401,7 @@ def prove_with_rs(params: Parameters, values_input: np.ndarray, values_aux: np.n
                   ctx: Context, return_h: bool = False):
     """create_proof(circuit, params, r, s): deterministic blinding.  Returns
     (public inputs [without ONE], Proof) like prover.rs:84-89."""
-    pk = params.load(ctx, getattr(params, "_checked", True))
+    pk = params.load(ctx)
     vi = np.ascontiguousarray(values_input, dtype=np.uint64)
     va = np.ascontiguousarray(values_aux, dtype=np.uint64)
     ra, sa = fr_raw(r), fr_raw(s)
@@ -412,7 +427,7 @@ def prove_batch(params: Parameters, witnesses, rs: Sequence[int], ss: Sequence[i
         raise ValueError("prove_batch: witnesses, rs and ss differ in length")
     if count == 0:
         return []
-    pk = params.load(ctx, getattr(params, "_checked", True))
+    pk = params.load(ctx)
     vis = [np.ascontiguousarray(w[0], dtype=np.uint64) for w in witnesses]
     vas = [np.ascontiguousarray(w[1], dtype=np.uint64) for w in witnesses]
     n_in, n_aux = vis[0].shape[0], vas[0].shape[0]
@@ -433,7 +448,7 @@ class ProveStream:
     While the stream is open the key is used through it only."""
 
     def __init__(self, params: Parameters, ctx: Context, depth: int = 0):
-        self._pk = params.load(ctx, getattr(params, "_checked", True))
+        self._pk = params.load(ctx)
         self._params = params
         self._h = C.c_void_p()
         self._inputs = {}
@@ -479,7 +494,9 @@ def prove(params: Parameters, values_input: np.ndarray, values_aux: np.ndarray, 
 
 def verify(vk: VK, proof: Proof, inputs: np.ndarray) -> bool:
     """`verify` of verifier.rs:75-81.  inputs: uint64[n,4] Montgomery, without ONE.
-    Raises on a length mismatch (the reference panics through .unwrap())."""
+    Raises on a length mismatch, and on limbs that are not reduced field elements or points that are not on
+    their curve in the key, the proof or the inputs (the reference panics there through `.unwrap()`:
+    verifier.rs:80, group.rs:53-65,87-105, mod.rs:105-120)."""
     raw = vk.to_raw()
     ins = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, 4)
     ok = C.c_int()

@@ -105,6 +105,13 @@ int fb_circuit_shape(const fb_circuit* c, uint32_t* n_in, uint32_t* n_aux, uint3
                      uint64_t* nnz);
 
 /* ---- proving key ----------------------------------------------------------- */
+/* `checked` carries the two booleans of Parameters::read(reader, disallow_points_at_infinity, checked)
+ * (mod.rs:159-175; bellman_ce 0.3.5 Parameters::read): bit 0 = checked (every query point must be on its curve
+ * and, for G2, in the r-torsion subgroup: [r]P == O), bit 1 = disallow_points_at_infinity.  Always enforced, as by
+ * pairing_ce's decoder: coordinates < p, no compression flag, an infinity encoding with every other bit zero;
+ * the verifying-key points are always read checked and the ic points may not be at infinity (VerifyingKey::read). */
+#define FB_LOAD_CHECKED 1
+#define FB_LOAD_NO_INFINITY 2
 int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uint8_t* gates_brotli,
                size_t glen, uint32_t num_gates, int checked, fb_pk** out);
 int fb_pk_load_circuit(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,

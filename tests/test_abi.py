@@ -137,12 +137,96 @@ def test_host_verify_and_framing_on_golden(golden):
     inputs = fr_np([int(golden["inputs"][1], 16)])
     assert fb.verify(vk, proof, inputs) is True
     assert fb.verify(vk, proof, fr_np([int(golden["inputs"][1], 16) ^ 1])) is False
+    # a different, well-formed proof (C replaced by A: on the curve, wrong statement) is rejected ...
+    swapped = proof.to_raw()[:192] + proof.to_raw()[:64]
+    assert fb.verify(vk, fb.Proof.from_raw(swapped), inputs) is False
+    # ... while malformed encodings are errors, as in the reference (`from_raw_uncompressed_le(..).unwrap()`,
+    # group.rs:53-65; `from_raw_repr(..).unwrap()`, mod.rs:105-120): a point off its curve,
     tampered = bytearray(proof.to_raw())
     tampered[200] ^= 1
-    assert fb.verify(vk, fb.Proof.from_raw(bytes(tampered)), inputs) is False
+    with pytest.raises(fb.native.FbError) as e:
+        fb.verify(vk, fb.Proof.from_raw(bytes(tampered)), inputs)
+    assert e.value.code == -3 and "curve" in str(e.value)
+    # limbs that are not a reduced field element: x + r is another bit pattern of the same residue and must not
+    # verify for the same statement (input aliasing),
+    x_mont = int.from_bytes(inputs[0].tobytes(), "little")
+    alias = np.frombuffer((x_mont + bn.R).to_bytes(32, "little"), dtype=np.uint64).reshape(1, 4).copy()
+    with pytest.raises(fb.native.FbError) as e:
+        fb.verify(vk, proof, alias)
+    assert e.value.code == -3 and "input" in str(e.value)
+    # the same for a proof coordinate (A.x + p) and for a verifying-key point off the curve
+    ax = int.from_bytes(proof.to_raw()[:32], "little") + bn.P
+    if ax < 1 << 256:
+        with pytest.raises(fb.native.FbError):
+            fb.verify(vk, fb.Proof.from_raw(ax.to_bytes(32, "little") + proof.to_raw()[32:]), inputs)
+    bad_vk = fb.VK.deserialize(vk.serialize())
+    bad_vk.ic[1] = fb.G1Point(bad_vk.ic[1].raw[:32] + bad_vk.ic[0].raw[32:])
+    with pytest.raises(fb.native.FbError) as e:
+        fb.verify(bad_vk, proof, inputs)
+    assert e.value.code == -3
     with pytest.raises(fb.native.FbError) as e:   # reference: MalformedVerifyingKey -> panic
         fb.verify(vk, proof, fr_np([1, 2]))
     assert e.value.code == -7
+
+
+def g2_point_outside_the_subgroup(seed=1):
+    """A point of the twist curve y^2 = x^3 + 3/(9+u) that is NOT in the r-torsion subgroup (the cofactor of
+    BN254's G2 is ~2^254, so the first curve point found by trying x values is outside)."""
+    b2 = bn.OPS2.b
+
+    def f2_sqrt(a):   # p = 3 mod 4 (Adj, Rodriguez-Henriquez alg. 9)
+        a1 = bn.f2_pow(a, (bn.P - 3) // 4)
+        alpha = bn.f2_mul(bn.f2_sqr(a1), a)
+        a0 = bn.f2_mul(bn.f2_pow(alpha, bn.P), alpha)
+        if a0 == (bn.P - 1, 0):
+            return None
+        x0 = bn.f2_mul(a1, a)
+        if alpha == (bn.P - 1, 0):
+            return bn.f2_mul((0, 1), x0)
+        b = bn.f2_pow(bn.f2_add((1, 0), alpha), (bn.P - 1) // 2)
+        return bn.f2_mul(b, x0)
+
+    x = (seed, 1)
+    while True:
+        rhs = bn.f2_add(bn.f2_mul(bn.f2_sqr(x), x), b2)
+        y = f2_sqrt(rhs)
+        if y is not None and bn.f2_sqr(y) == rhs:
+            pt = (x, y)
+            assert bn.on_curve(bn.OPS2, pt)
+            if bn.pt_mul(bn.OPS2, pt, bn.R) is not None:
+                return pt
+        x = (x[0] + 1, 1)
+
+
+def test_verifying_key_points_are_read_checked(golden):
+    """bellman's VerifyingKey::read decodes with `into_affine()` (on curve AND in the r-torsion subgroup), and the
+    decoder itself rejects compression flags and dirty infinity encodings: the host decoder used for the
+    verifying-key prefix (here through fb_prove_finish) does the same."""
+    import fawkes_crypto_b200 as fb
+    from tests.dist_helpers import shard_partials
+    pb = bytearray(bytes.fromhex(golden["bellman_params_hex"]))
+    parts = np.frombuffer(b"".join(shard_partials(golden, rank, 2) for rank in range(2)), dtype=np.uint8).copy()
+    r, s = fr_np([int(golden["r"], 16)])[0], fr_np([int(golden["s"], 16)])[0]
+    out = np.zeros(256, dtype=np.uint8)
+
+    def finish(buf):
+        b = bytes(buf)
+        return fb.native.lib.fb_prove_finish(fb.native.ptr(b), len(b), parts.ctypes.data, 2, r.ctypes.data,
+                                             s.ctypes.data, out.ctypes.data)
+
+    assert finish(pb) == 0
+    bad = bytearray(pb)
+    bad[128:256] = codec.g2_uncompressed(g2_point_outside_the_subgroup())      # beta_g2: on the curve, wrong subgroup
+    assert finish(bad) == -3
+    bad = bytearray(pb)
+    bad[0] |= 0x80                                                              # compression flag on alpha_g1
+    assert finish(bad) == -3
+    bad = bytearray(pb)
+    bad[384:448] = bytes([0x40]) + bytes(62) + bytes([1])                       # delta_g1: dirty infinity encoding
+    assert finish(bad) == -3
+    bad = bytearray(pb)
+    bad[64:128] = (bn.P).to_bytes(32, "big") + bad[96:128]                      # beta_g1.x = p: not a field element
+    assert finish(bad) == -3
 
 
 def test_prove_finish_combines_partials(golden):

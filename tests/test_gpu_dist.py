@@ -41,20 +41,30 @@ def _worker(rank, world, port, q):
     pk = C.c_void_p()
     pb = params.bellman_bytes
     fb.native.check(lib.fb_pk_load_shard(ctx.handle, fb.native.ptr(pb), len(pb), circ.handle, 1, rank, world, C.byref(pk)))
+    # library-side collective prove: every rank calls fb_prove on its shard of the key; the 640-byte partial sums
+    # travel over the library's own NCCL communicator and EVERY rank returns the proof
+    r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
+    out = np.zeros(256, dtype=np.uint8)
+    fb.native.check(lib.fb_prove(ctx.handle, pk, wi.ctypes.data, wi.shape[0], wa.ctypes.data, wa.shape[0],
+                                 r.ctypes.data, s.ctypes.data, out.ctypes.data, None))
+    # same through the device-resident entry point
+    w_dev = torch.from_numpy(np.concatenate([wi, wa]).view(np.int64)).cuda()
+    out_dev = np.zeros(256, dtype=np.uint8)
+    fb.native.check(lib.fb_prove_device(ctx.handle, pk, w_dev.data_ptr(), r.ctypes.data, s.ctypes.data,
+                                        out_dev.ctypes.data))
+    # and with the caller's own transport: fb_prove_partial + all-gather + fb_prove_finish
     partial = np.zeros(640, dtype=np.uint8)
     fb.native.check(lib.fb_prove_partial(ctx.handle, pk, wi.ctypes.data, wi.shape[0], wa.ctypes.data, wa.shape[0],
                                          partial.ctypes.data))
     gathered = torch.empty((world, 640), dtype=torch.uint8, device="cuda")
     dist.all_gather_into_tensor(gathered, torch.from_numpy(partial).cuda())
-    ok = None
-    if rank == 0:
-        r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
-        out = np.zeros(256, dtype=np.uint8)
-        parts = gathered.cpu().numpy()
-        fb.native.check(lib.fb_prove_finish(fb.native.ptr(pb), 580, parts.ctypes.data, world, r.ctypes.data,
-                                            s.ctypes.data, out.ctypes.data))
-        _, ref = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)   # unsharded key, same GPU
-        ok = bool(out.tobytes() == ref.to_raw()) and fb.verify(params.get_vk(), ref, wi[1:])
+    parts = gathered.cpu().numpy()
+    out_manual = np.zeros(256, dtype=np.uint8)
+    fb.native.check(lib.fb_prove_finish(fb.native.ptr(pb), 580, parts.ctypes.data, world, r.ctypes.data,
+                                        s.ctypes.data, out_manual.ctypes.data))
+    _, ref = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)   # unsharded key, same GPU
+    ok = bool(out.tobytes() == ref.to_raw() and out_dev.tobytes() == ref.to_raw() and
+              out_manual.tobytes() == ref.to_raw()) and fb.verify(params.get_vk(), ref, wi[1:])
     dist.barrier()
     lib.fb_pk_free(pk)
     dist.destroy_process_group()
@@ -75,4 +85,4 @@ def test_two_gpu_distributed_prove():
     res = dict(q.get(timeout=600) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
-    assert res[0] is True
+    assert res[0] is True and res[1] is True   # every rank holds the proof

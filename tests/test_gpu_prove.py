@@ -106,6 +106,104 @@ def test_error_paths(ctx):
     assert e.value.code == -3
 
 
+def test_parameters_read_flags(ctx):
+    """Parameters::read(reader, disallow_points_at_infinity, checked) (mod.rs:159-175): `checked` adds the curve and
+    the r-torsion test to every query point (the subgroup test matters for G2 only), `disallow_points_at_infinity`
+    rejects the infinity encoding, and the decoder always rejects a dirty infinity encoding."""
+    import struct
+    import fawkes_crypto_b200 as fb
+    from tests.test_abi import g2_point_outside_the_subgroup
+    seed = synth.SEED_BASE + 301
+    gates, inp, aux, td, r, s, P = oracle_case(20, seed)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    blob = codec.brotli_compress(raw)
+    good = codec.bellman_params_bytes(P)
+    framed = lambda pb: fb.Parameters(pb, len(gates), blob).write()
+    # section offsets of the bellman body
+    n_ic = struct.unpack_from(">I", good, 576)[0]
+    pos = 580 + 64 * n_ic
+    off = {}
+    for name, sz in (("h", 64), ("l", 64), ("a", 64), ("b_g1", 64), ("b_g2", 128)):
+        n = struct.unpack_from(">I", good, pos)[0]
+        off[name] = pos + 4
+        pos += 4 + n * sz
+    # 1. a b_g2 query point on the twist curve but outside the subgroup: only a checked read notices
+    bad = bytearray(good)
+    bad[off["b_g2"]:off["b_g2"] + 128] = codec.g2_uncompressed(g2_point_outside_the_subgroup(3))
+    with pytest.raises(fb.native.FbError) as e:
+        fb.Parameters.read(framed(bytes(bad)), False, True).load(ctx)
+    assert e.value.code == -3 and "r-torsion" in str(e.value)
+    p_unchecked = fb.Parameters.read(framed(bytes(bad)), False, False)
+    p_unchecked.load(ctx)
+    p_unchecked.unload()
+    # 2. a point at infinity in the h query: fine by default, an error with disallow_points_at_infinity
+    inf = bytearray(good)
+    inf[off["h"]:off["h"] + 64] = bytes([0x40]) + bytes(63)
+    p_inf = fb.Parameters.read(framed(bytes(inf)), False, True)
+    p_inf.load(ctx)
+    p_inf.unload()
+    with pytest.raises(fb.native.FbError) as e:
+        fb.Parameters.read(framed(bytes(inf)), True, True).load(ctx)
+    assert e.value.code == -3 and "infinity" in str(e.value)
+    # 3. infinity flag with other bits set: never accepted
+    inf[off["h"] + 40] = 7
+    with pytest.raises(fb.native.FbError) as e:
+        fb.Parameters.read(framed(bytes(inf)), False, False).load(ctx)
+    assert e.value.code == -3
+    # 4. an l query point off the curve: only a checked read notices
+    offc = bytearray(good)
+    offc[off["l"] + 63] ^= 1
+    with pytest.raises(fb.native.FbError):
+        fb.Parameters.read(framed(bytes(offc)), False, True).load(ctx)
+    # 5. one resident key per Parameters: another context / shard needs unload() first
+    params = fb.Parameters.read(framed(good))
+    params.load(ctx)
+    with pytest.raises(ValueError):
+        params.load(ctx, shard=1, nshards=2)
+    inputs, proof = fb.groth16.prove_with_rs(params, fr_np(inp), fr_np(aux), r, s, ctx)
+    assert proof.to_raw() == codec.proof_raw(og.prove(P, gates, inp, aux, r, s))
+    params.unload()
+
+
+def test_prove_rejects_a_key_of_another_context(ctx):
+    import ctypes as C
+    import fawkes_crypto_b200 as fb
+    seed = synth.SEED_BASE + 302
+    gates, inp, aux, td, r, s, P = oracle_case(12, seed)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
+    pk = params.load(ctx)
+    other = fb.Context(ctx.device)
+    vi, va = fr_np(inp), fr_np(aux)
+    ra, sa = fr_np([r])[0], fr_np([s])[0]
+    out = np.zeros(256, dtype=np.uint8)
+    rc = fb.native.lib.fb_prove(other.handle, pk, vi.ctypes.data, 2, va.ctypes.data, va.shape[0], ra.ctypes.data,
+                                sa.ctypes.data, out.ctypes.data, None)
+    assert rc == -1 and "different fb_ctx" in fb.native.last_error()
+    other.close()
+    params.unload()
+
+
+def test_corrupt_gate_stream_is_an_error(ctx):
+    """A gate blob that is not valid brotli, is cut short, or expands beyond what the announced gate count can
+    hold is FB_ERR_FORMAT at key load (never a silently shorter circuit, never unbounded growth)."""
+    import fawkes_crypto_b200 as fb
+    gates, inp, aux = synth.synth_circuit(200, 11)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    blob = codec.brotli_compress(raw)
+    for bad in (blob[:len(blob) // 2], b"\xff" * 64 + blob[64:]):
+        with pytest.raises(fb.native.FbError) as e:
+            fb.Circuit.from_gates_blob(bad, len(gates), 2, len(aux), ctx)
+        assert e.value.code == -3
+        with pytest.raises(fb.native.FbError) as e:
+            fb.Circuit.from_gates_blob(bad, len(gates), 2, len(aux))
+        assert e.value.code == -3
+    bomb = codec.brotli_compress(bytes(64 << 20))       # 64 MiB of zeros in a few hundred bytes
+    with pytest.raises(fb.native.FbError) as e:
+        fb.Circuit.from_gates_blob(bomb, 3, 2, 5)
+    assert e.value.code == -3 and "expands beyond" in str(e.value)
+
+
 def test_golden_fixture_through_blob_path(ctx):
     """Committed golden vector (tests/golden, made by tools/gen_golden.py from the oracle): raw
     Parameters bytes + brotli gate blob -> fb_pk_load -> proof bytes."""
@@ -266,12 +364,37 @@ def test_prove_2_20_bytes_equal_cpp_oracle(ctx):
     import fawkes_crypto_b200 as fb
     import bench
     from oracle import cpu
+    import hashlib
     circ, params, tdi, _ = bench.make_case(fb, ctx, 20)
     wi, wa = circ.witness()
     inputs, proof = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
     assert fb.verify(params.get_vk(), proof, inputs)
-    cproof, _ = bench.cpu_prove_once(fb, circ, params, tdi, cpu.hw_threads())
+    # the oracle's own circuit and witness (oracle/cpu_setup.cpp), the keys fb_setup produced
+    seed = bench.SEED_BASE + bench.cfg_number(20)
+    ccirc = cpu.Circuit.synthetic(1 << 20, seed)
+    assert np.array_equal(ccirc.aux, wa) and np.array_equal(ccirc.inputs, wi)
+    ctd = cpu.synth_trapdoor(seed)
+    cproof, _, _ = cpu.prove_circuit(params.bellman_bytes, ccirc, ctd[5], ctd[6], cpu.hw_threads())
     assert proof.to_raw() == cproof
+    # committed golden (tools/gen_golden_synth.py: CPU circuit + CPU setup + CPU prove)
+    g = bench.golden_synth(20)
+    assert hashlib.sha256(proof.to_raw()).hexdigest() == g["proof_sha256"]
+    assert hashlib.sha256(params.bellman_bytes).hexdigest() == g["params_sha256"]    # fb_setup == CPU setup, 335 MB
+    params.unload()
+
+
+@pytest.mark.parametrize("log_rows", [12, 16])
+def test_gpu_setup_and_prove_equal_cpu_golden_small(ctx, log_rows):
+    """tests/golden/synth_proofs.json at 2^12 and 2^16 rows: GPU setup digest and GPU proof bytes equal the CPU chain's."""
+    import hashlib
+    import fawkes_crypto_b200 as fb
+    import bench
+    circ, params, tdi, _ = bench.make_case(fb, ctx, log_rows)
+    wi, wa = circ.witness()
+    _, proof = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
+    g = bench.golden_synth(log_rows)
+    assert proof.to_raw().hex() == g["proof_raw_hex"]
+    assert hashlib.sha256(params.bellman_bytes).hexdigest() == g["params_sha256"]
     params.unload()
 
 
@@ -359,8 +482,8 @@ def test_cfg2_eddsa_poseidon_batch_setup_prove_verify(ctx):
 
 
 def test_prove_2_24_full_size_verifies(ctx):
-    """BASELINE configs[3] at full size (2^24 rows, 75 GB resident key with window tables): the proof passes
-    the pairing check (a size-independent end-to-end property: A, B and C are right only if all five
+    """BASELINE configs[3] at full size (2^24 rows, 75 GB resident key with window tables): the proof is BYTE-IDENTICAL to the CPU oracle's
+    (committed golden), passes the pairing check (a size-independent end-to-end property: A, B and C are right only if all five
     MSMs over 16.7 M points and the seven 2^24-point transforms are), the public input is echoed, a
     tampered input fails, and proving twice gives the same bytes."""
     import fawkes_crypto_b200 as fb
@@ -376,4 +499,11 @@ def test_prove_2_24_full_size_verifies(ctx):
     assert not fb.verify(params.get_vk(), proof, bad)
     _, proof2 = fb.groth16.prove_with_rs(params, wi, wa, tdi[5], tdi[6], ctx)
     assert proof2.to_raw() == proof.to_raw()
+    # byte parity at the full size: the committed golden is the CPU oracle's proof of this circuit, witness, r, s
+    # under the CPU oracle's own setup (tools/gen_golden_synth.py, ~10 CPU-minutes); the digest of the 5.4 GB
+    # Parameters byte string says fb_setup reproduced every one of the 84 M key points
+    import hashlib
+    g = bench.golden_synth(24)
+    assert proof.to_raw().hex() == g["proof_raw_hex"]
+    assert hashlib.sha256(params.bellman_bytes).hexdigest() == g["params_sha256"]
     params.unload()
