@@ -111,6 +111,32 @@ struct Timing {
 };
 static thread_local Timing g_timing;  // per calling thread (fb_prove_batch proves on several)
 
+// log2 of the number of ranks the R1CS rows and the H pipeline of a key are sharded over (0 = replicated):
+// world = nshards = 2^g ranks with an NCCL exchange, shard = rank, and a domain large enough.
+int key_dist_g(const Ctx* ctx, int k, int shard, int nshards) {
+  if (!(nshards > 1 && ctx->exchange && ctx->world == nshards && ctx->rank == shard && (nshards & (nshards - 1)) == 0))
+    return 0;
+  int g = 0;
+  while ((1 << g) < nshards) g++;
+  NttDomain probe;
+  probe.k = k;
+  const char* env = getenv("FB_DIST_NTT_MIN_LOG");
+  const int min_log = env ? atoi(env) : 20;
+  return (probe.dist_supported(g) && k >= min_log) ? g : 0;
+}
+// positions [lo, lo + cnt) of the bit-reversed h array a shard keeps
+void key_h_range(uint64_t m, int dist_g, int shard, int nshards, uint64_t* lo, uint64_t* cnt) {
+  const uint64_t nh = m - 1;
+  if (dist_g) {  // H comes out of the distributed pipeline in block layout: positions [rank*ml, (rank+1)*ml)
+    const uint64_t ml = m >> dist_g;
+    *lo = (uint64_t)shard * ml;
+    *cnt = std::min<uint64_t>(ml, nh - *lo);
+  } else {
+    *lo = nh * shard / nshards;
+    *cnt = nh * (shard + 1) / nshards - *lo;
+  }
+}
+
 static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circuit* circ, int checked,
                          int shard, int nshards, bool allow_tables, bool* used_tables, ProvingKey** out) {
   if (!ctx || !params || !circ || !out || nshards < 1 || shard < 0 || shard >= nshards) {
@@ -152,16 +178,7 @@ static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circ
     return FB_ERR_FORMAT;
   }
   // distributed H pipeline: world = nshards = 2^g ranks with an NCCL exchange and a domain large enough
-  int dist_g = 0;
-  if (nshards > 1 && ctx->exchange && ctx->world == nshards && ctx->rank == shard && (nshards & (nshards - 1)) == 0) {
-    int g = 0;
-    while ((1 << g) < nshards) g++;
-    NttDomain probe;
-    probe.k = k;
-    const char* env = getenv("FB_DIST_NTT_MIN_LOG");
-    const int min_log = env ? atoi(env) : 20;
-    if (probe.dist_supported(g) && k >= min_log) dist_g = g;
-  }
+  const int dist_g = key_dist_g(ctx, k, shard, nshards);
   pk->dist_g = dist_g;
   const uint64_t ml = dist_g ? (m >> dist_g) : m;  // local length of the evaluation arrays
   cudaStream_t st = ctx->stream;
@@ -318,7 +335,7 @@ static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circ
   int arc = 0;
   for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_plans[i], 1, i == 3);
   if (!arc && g_msm_batch_affine)  // optional buffers: a scratch that cannot get them accumulates in XYZZ only
-    for (int i = 0; i < 4; i++) pk->msm[i].alloc_batch_affine(&msm_plans[i], 1, i == 3);
+    for (int i = g_msm_batch_affine == 3 ? 3 : 0; i < 4; i++) pk->msm[i].alloc_batch_affine(&msm_plans[i], 1, i == 3);
   if (arc != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
@@ -995,7 +1012,7 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
   info->msm_window_bits = pk->plan_h.c;
   info->msm_windows = pk->plan_h.W;
   info->msm_tables = pk->plan_h.table ? 1 : 0;
-  info->msm_batch_affine = pk->msm[0].ba_cap ? 1 : 0;
+  info->msm_batch_affine = (pk->msm[0].ba_cap || pk->msm[3].ba_cap) ? 1 : 0;
   info->table_bytes = pk->table_bytes;
   return FB_OK;
 }
@@ -1390,7 +1407,7 @@ uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
 void fb_set_prove_graph(int on) { fb::g_prove_graph.store(on ? 1 : 0); }
-void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 2) ? 0 : on; }
+void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 3) ? 0 : on; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {

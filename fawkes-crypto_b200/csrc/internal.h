@@ -133,6 +133,8 @@ struct ParamsView {  // offsets into bellman Parameters bytes
   uint32_t n_ic, n_h, n_l, n_a, n_b1, n_b2;
 };
 int parse_params(const uint8_t* b, size_t len, ParamsView& v);  // api.cu
+int key_dist_g(const Ctx* ctx, int k, int shard, int nshards);    // api.cu: how a key on this context shards H
+void key_h_range(uint64_t m, int dist_g, int shard, int nshards, uint64_t* lo, uint64_t* cnt);
 
 // pk.cu
 int parse_gates_to_csr(const uint8_t* raw, size_t len, uint32_t n_in, uint32_t n_aux, HostCsr& out);

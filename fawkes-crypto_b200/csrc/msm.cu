@@ -764,7 +764,11 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   const uint64_t N = (uint64_t)p.n * p.W;
   const int kind = sizeof(F) == sizeof(Fq) ? KSTAT_ACC_G1 : KSTAT_ACC_G2;
   // ---- batch-affine rounds: sorted entries -> ~N / 2^R affine points, still grouped by bucket
-  int R = (g_msm_batch_affine && s.ba_cap >= N) ? p.ba_rounds() : 0;
+  // mode 3: G2 only (an Fq2 add is 2.5x the MACs of an Fq one for 2x the bytes, so the rounds pay there first)
+  const bool ba_on = g_msm_batch_affine == 1 || g_msm_batch_affine == 2 ||
+                     (g_msm_batch_affine == 3 && sizeof(F) == sizeof(Fq2));
+  int R = (ba_on && s.ba_cap >= N) ? p.ba_rounds() : 0;
+  if (const char* e = getenv("FB_MSM_BA_ROUNDS")) R = std::min(R, atoi(e));
   const uint32_t* offsets = s.offsets;
   const Affine<F>* acc_pts = bases;
   int task_log = p.task_log;

@@ -178,11 +178,19 @@ int fb_test_fixed_base(fb_ctx* ctx_, int group, const uint64_t* scalars, uint64_
   return rc;
 }
 
-int fb_setup(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t trapdoor[5][4],
-             uint8_t** params_out, size_t* len_out) {
+// shard / nshards: nshards == 1 generates every point.  Otherwise only the points fb_pk_load_shard(shard, nshards)
+// on this context keeps are generated (contiguous slices of l, a, b_g1, b_g2; for h the bit-reversed positions of
+// the shard's range); every other query point is written as the point at infinity, so the output is still a
+// well-formed bellman Parameters byte string of the full size -- the fixed-base work, which is all of the
+// GPU time of a setup, drops by nshards.
+static int setup_impl(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t trapdoor[5][4], int shard, int nshards,
+                      uint8_t** params_out, size_t* len_out) {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   const Circuit* c = reinterpret_cast<const Circuit*>(circuit);
-  if (!ctx || !c || !trapdoor || !params_out || !len_out) { set_error("fb_setup: bad argument"); return FB_ERR_ARG; }
+  if (!ctx || !c || !trapdoor || !params_out || !len_out || nshards < 1 || shard < 0 || shard >= nshards) {
+    set_error("fb_setup: bad argument");
+    return FB_ERR_ARG;
+  }
   FB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const HostCsr& csr = c->csr;
@@ -271,6 +279,40 @@ int fb_setup(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t trapdoor[5]
     if (!rc) rc = fbk.run(group, s, n, out + pos, 1);
     pos += n * (group == 1 ? 64 : 128);
   };
+  auto fill_inf = [&](uint8_t* p, uint64_t n, size_t psz) {
+    memset(p, 0, n * psz);
+    for (uint64_t i = 0; i < n; i++) p[i * psz] = 0x40;
+  };
+  // a query of which this shard keeps the slice [n*shard/nshards, n*(shard+1)/nshards)
+  auto emit_slice = [&](int group, const Fr* s, uint64_t n) {
+    const size_t psz = group == 1 ? 64 : 128;
+    if (nshards == 1) { emit(group, s, n); return; }
+    const uint64_t lo = n * shard / nshards, hi = n * (shard + 1) / nshards;
+    fill_inf(out + pos, lo, psz);
+    if (!rc) rc = fbk.run(group, s + lo, hi - lo, out + pos + lo * psz, 1);
+    fill_inf(out + pos + hi * psz, n - hi, psz);
+    pos += n * psz;
+  };
+  // h: the loader keeps positions [h_lo, h_lo + h_cnt) of the BIT-REVERSED array, i.e. coefficient i = brev(p)
+  auto emit_h = [&](const Fr* s, uint64_t n) {
+    if (nshards == 1) { emit(1, s, n); return; }
+    uint64_t h_lo, h_cnt;
+    key_h_range(m, key_dist_g(ctx, k, shard, nshards), shard, nshards, &h_lo, &h_cnt);
+    std::vector<Fr> sel(h_cnt);
+    std::vector<uint32_t> idx(h_cnt);
+    for (uint64_t p = 0; p < h_cnt; p++) {
+      uint64_t i = 0, q = h_lo + p;
+      for (int b = 0; b < k; b++) i |= ((q >> b) & 1) << (k - 1 - b);
+      idx[p] = (uint32_t)i;      // i < m - 1 for every position the loader reads (position of m-1 is m-1 itself)
+      sel[p] = i < n ? s[i] : Fr::zero();
+    }
+    std::vector<uint8_t> pts(h_cnt * 64);
+    if (!rc) rc = fbk.run(1, sel.data(), h_cnt, pts.data(), 1);
+    fill_inf(out + pos, n, 64);
+    for (uint64_t p = 0; p < h_cnt; p++)
+      if (idx[p] < n) memcpy(out + pos + (uint64_t)idx[p] * 64, pts.data() + p * 64, 64);
+    pos += n * 64;
+  };
   Fr vk1[3] = {F_of(alpha), F_of(beta), F_of(delta)};
   Fr vk2[3] = {F_of(beta), F_of(gamma), F_of(delta)};
   emit(1, &vk1[0], 1);  // alpha_g1
@@ -280,16 +322,26 @@ int fb_setup(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t trapdoor[5]
   emit(1, &vk1[2], 1);  // delta_g1
   emit(2, &vk2[2], 1);  // delta_g2
   len_be(n_in); emit(1, ic_s.data(), n_in);
-  len_be(n_h); emit(1, h_s.data(), n_h);
-  len_be(n_aux); emit(1, l_s.data(), n_aux);
-  len_be(n_a); emit(1, a_s.data(), n_a);
-  len_be(n_b); emit(1, b_s.data(), n_b);
-  len_be(n_b); emit(2, b_s.data(), n_b);
+  len_be(n_h); emit_h(h_s.data(), n_h);
+  len_be(n_aux); emit_slice(1, l_s.data(), n_aux);
+  len_be(n_a); emit_slice(1, a_s.data(), n_a);
+  len_be(n_b); emit_slice(1, b_s.data(), n_b);
+  len_be(n_b); emit_slice(2, b_s.data(), n_b);
   fbk.release();
   if (rc) { free(out); return rc; }
   *params_out = out;
   *len_out = total;
   return FB_OK;
+}
+
+int fb_setup(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4], uint8_t** params_out,
+             size_t* len_out) {
+  return setup_impl(ctx, circuit, trapdoor, 0, 1, params_out, len_out);
+}
+
+int fb_setup_shard(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4], int shard, int nshards,
+                   uint8_t** params_out, size_t* len_out) {
+  return setup_impl(ctx, circuit, trapdoor, shard, nshards, params_out, len_out);
 }
 
 }  // extern "C"

@@ -380,13 +380,17 @@ def _sample_fr() -> int:
 
 
 def setup(circuit: Circuit, ctx: Context, trapdoor: Optional[Sequence[int]] = None, num_gates: Optional[int] = None,
-          gates_blob: bytes = b"", const_tracker=()) -> Parameters:
+          gates_blob: bytes = b"", const_tracker=(), shard: int = 0, nshards: int = 1) -> Parameters:
     """`setup(circuit)` of setup.rs:7-35 for an already-built R1CS.  trapdoor = (alpha, beta,
-    gamma, delta, tau) canonical integers; sampled from the OS when omitted."""
+    gamma, delta, tau) canonical integers; sampled from the OS when omitted.  nshards > 1: only the query points
+    of this rank's shard are generated (fb_setup_shard; every rank must pass the same trapdoor)."""
     td = list(trapdoor) if trapdoor is not None else [_sample_fr() for _ in range(5)]
     tda = fr_array(td)
     out, n = C.c_void_p(), C.c_size_t()
-    nv.check(nv.lib.fb_setup(ctx.handle, circuit.handle, nv.ptr(tda), C.byref(out), C.byref(n)))
+    if nshards == 1:
+        nv.check(nv.lib.fb_setup(ctx.handle, circuit.handle, nv.ptr(tda), C.byref(out), C.byref(n)))
+    else:
+        nv.check(nv.lib.fb_setup_shard(ctx.handle, circuit.handle, nv.ptr(tda), shard, nshards, C.byref(out), C.byref(n)))
     try:
         # ctypes.string_at takes a C int length: copy by hand so keys beyond 2 GiB survive
         data = np.empty(n.value, dtype=np.uint8)

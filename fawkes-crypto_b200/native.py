@@ -63,6 +63,7 @@ SIGNATURES = {
     "fb_prove_finish": (C.c_int, [vp, C.c_size_t, vp, C.c_int, vp, vp, vp]),
     "fb_prove_timings": (C.c_int, [vp, f32p]),
     "fb_setup": (C.c_int, [vp, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]),
+    "fb_setup_shard": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]),
     "fb_verify": (C.c_int, [vp, C.c_uint32, vp, vp, C.c_uint32, C.POINTER(C.c_int)]),
     "fb_circuit_synth": (C.c_int, [C.c_uint64, C.c_uint64, C.POINTER(vp)]),
     "fb_circuit_witness": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),

@@ -173,6 +173,12 @@ int fb_dist_init(fb_ctx* ctx, int rank, int world, const uint8_t id[128]);
  * ones.  Writes bellman-format Parameters bytes (free with fb_free). */
 int fb_setup(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4],
              uint8_t** params_out, size_t* len);
+/* Multi-GPU setup: the same byte string, but only the query points that fb_pk_load_shard(shard, nshards) on THIS
+ * context keeps are generated (the fixed-base work drops by nshards); every other query point is written as the
+ * point at infinity.  The verifying key and ic are complete on every rank.  Load the result with the same
+ * shard / nshards on the same context (after fb_dist_init, if the key is to shard its H pipeline too). */
+int fb_setup_shard(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4], int shard, int nshards,
+                   uint8_t** params_out, size_t* len);
 /* vk: alpha_g1 | beta_g2 | gamma_g2 | delta_g2 raw (64+128+128+128 B) then n_ic raw G1 (VK of
  * verifier.rs:12-18 in memory).  inputs: public inputs WITHOUT the leading ONE. */
 int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t proof_raw[256],
