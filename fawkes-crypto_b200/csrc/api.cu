@@ -62,6 +62,7 @@ __global__ void k_gather_bitrev(G1Affine* __restrict__ dst, const G1Affine* __re
 }
 
 static void free_host_tables(void* p);
+static void free_batch(void* p);
 static void* build_host_tables(const ProvingKey* pk);
 static void pk_release(ProvingKey* pk) {
   if (!pk) return;
@@ -80,6 +81,7 @@ static void pk_release(ProvingKey* pk) {
   cudaFree(pk->results);
   if (pk->results_host) cudaFreeHost(pk->results_host);
   for (auto& e : pk->msm_done) if (e) cudaEventDestroy(e);
+  if (pk->batch) free_batch(pk->batch);
   if (pk->graph_exec) cudaGraphExecDestroy(pk->graph_exec);
   if (pk->w_stage) cudaFreeHost(pk->w_stage);
   if (pk->is_slot) {
@@ -1081,6 +1083,7 @@ static ProvingKey* make_slot(const ProvingKey* pk) {
   s->is_slot = true;
   s->slots.clear();
   s->graph_exec = nullptr; s->w_stage = nullptr; s->graph_launches = 0; s->graph_failed = false;
+  s->batch = nullptr;
   s->w = nullptr; s->scratch = nullptr; s->results = nullptr; s->results_host = nullptr;
   for (auto& p : s->ev) p = nullptr;
   for (auto& p : s->xtmp) p = nullptr;
@@ -1109,6 +1112,202 @@ static ProvingKey* make_slot(const ProvingKey* pk) {
   return s;
 }
 
+// ---- batched proves of one small circuit (BASELINE configs[1]: 256 EdDSA proofs per run) ---------------------
+// The reference proves them one prove() call at a time (prover.rs:63-90).  One such prove is ~70 tiny kernels and
+// leaves a B200 idle, so a batch is proved as ONE set of launches carrying `P` proofs each: the witnesses are
+// uploaded as one [P][n_in + n_aux] array, R1CS evaluation and the seven transforms run with the proof index as
+// grid.y, and each of the five MSMs is one batched MSM -- the key's bases are shared, the buckets are keyed by
+// (proof, digit), so one digit sort, one bucket accumulation and one reduction serve all P proofs (msm.cuh:
+// MsmPlan::batched).  Host tails (Horner over the bit sums, r/s terms, affine conversion: ~0.4 ms per proof) run
+// on a pool of host threads for chunk k while the GPU works on chunk k + 1.
+}  // extern "C"
+
+namespace fb {
+struct BatchWork {
+  uint32_t P = 0;
+  uint64_t wstride = 0;
+  Fr* w = nullptr;
+  Fr* ev[3] = {nullptr, nullptr, nullptr};
+  MsmScratch msm[4];
+  size_t vmax = 0;                 // V entries per proof per MSM (max over the plans)
+  void* results = nullptr;         // device: 5 x P x vmax G2XYZZ-sized slots
+  void* results_host[2] = {nullptr, nullptr};
+  Fr* w_stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2][5];
+  cudaEvent_t uploaded[2];
+  cudaEvent_t start = nullptr;
+  bool used[2] = {false, false};
+  bool ok = false;
+  void release() {
+    cudaFree(w);
+    for (auto& p : ev) cudaFree(p);
+    for (auto& m : msm) m.release();
+    cudaFree(results);
+    for (auto& p : results_host) if (p) cudaFreeHost(p);
+    for (auto& p : w_stage) if (p) cudaFreeHost(p);
+    if (ok) {
+      for (auto& q : done) for (auto& e : q) cudaEventDestroy(e);
+      for (auto& e : uploaded) cudaEventDestroy(e);
+      cudaEventDestroy(start);
+    }
+  }
+};
+static void free_batch(void* p) {
+  BatchWork* b = reinterpret_cast<BatchWork*>(p);
+  if (b) { b->release(); delete b; }
+}
+
+static BatchWork* make_batch(ProvingKey* pk, uint32_t P) {
+  BatchWork* b = new BatchWork();
+  b->P = P;
+  b->wstride = (uint64_t)pk->n_in + pk->n_aux;
+  const MsmPlan plans[4] = {pk->plan_h.batched(P, pk->m), pk->plan_l.batched(P, b->wstride), pk->plan_a.batched(P, b->wstride),
+                            pk->plan_b.batched(P, b->wstride)};
+  for (const MsmPlan& p : plans) b->vmax = std::max<size_t>(b->vmax, (size_t)p.vbits_per_set());
+  bool ok = cudaMalloc(&b->w, std::max<size_t>(P * b->wstride, 1) * sizeof(Fr)) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; i++) ok = cudaMalloc(&b->ev[i], (size_t)P * pk->m * sizeof(Fr)) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; i++) ok = b->msm[i].alloc(&plans[i], 1, i == 3) == 0;
+  const size_t rbytes = 5 * (size_t)P * b->vmax * sizeof(G2XYZZ);
+  ok = ok && cudaMalloc(&b->results, rbytes) == cudaSuccess;
+  for (int q = 0; q < 2 && ok; q++) {
+    ok = cudaMallocHost(&b->results_host[q], rbytes) == cudaSuccess &&
+         cudaMallocHost(&b->w_stage[q], std::max<size_t>(P * b->wstride, 1) * sizeof(Fr)) == cudaSuccess;
+  }
+  if (ok) {
+    for (auto& q : b->done) for (auto& e : q) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : b->uploaded) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&b->start, cudaEventDisableTiming) == cudaSuccess;
+    b->ok = true;
+  }
+  if (!ok) {
+    cudaGetLastError();
+    free_batch(b);
+    return nullptr;
+  }
+  return b;
+}
+
+static int prove_batched(Ctx* ctx, ProvingKey* pk, uint32_t count, const uint64_t* const* inputs, const uint64_t* const* aux,
+                         const uint64_t* r, const uint64_t* s, uint8_t* proofs_raw) {
+  FB_CUDA(cudaSetDevice(ctx->device));
+  uint32_t P = 128;  // measured on configs[1] (256 proofs): 32 -> 0.28, 64 -> 0.20, 128 -> 0.18, 256 -> 0.20 ms per proof
+  if (const char* e = getenv("FB_BATCH_P")) P = (uint32_t)std::max(1, std::min(1024, atoi(e)));
+  P = std::min(P, count);
+  BatchWork* bw = reinterpret_cast<BatchWork*>(pk->batch);
+  if (bw && bw->P < P) { free_batch(bw); bw = nullptr; pk->batch = nullptr; }
+  if (!bw) {
+    bw = make_batch(pk, P);
+    if (!bw) { set_error("fb_prove_batch: cannot allocate the workspaces of a %u-proof batch", P); return FB_ERR_CUDA; }
+    pk->batch = bw;
+  }
+  P = bw->P;
+  cudaStream_t st = ctx->stream, sL = ctx->aux[0], sA = ctx->aux[1], sB = ctx->aux[2];
+  const uint64_t m = pk->m, ws = bw->wstride;
+  const size_t slot_elems = (size_t)P * bw->vmax;   // G2XYZZ-sized elements per MSM slot
+  auto dslot = [&](int i) { return reinterpret_cast<G2XYZZ*>(bw->results) + (size_t)i * slot_elems; };
+  auto hslot = [&](int q, int i) { return reinterpret_cast<G2XYZZ*>(bw->results_host[q]) + (size_t)i * slot_elems; };
+  VkPoints vk{pk->alpha_g1, pk->beta_g1, pk->delta_g1, pk->beta_g2, pk->delta_g2};
+  const KeyTables* kt = reinterpret_cast<const KeyTables*>(pk->host_tables);
+  const uint32_t nchunks = (count + P - 1) / P;
+  int host_threads = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+  if (const char* e = getenv("FB_BATCH_HOST_THREADS")) host_threads = std::max(1, atoi(e));
+
+  auto enqueue = [&](uint32_t k) -> int {
+    const int q = (int)(k & 1);
+    const uint32_t lo = k * P, cnt = std::min(P, count - lo);
+    if (bw->used[q]) FB_CUDA(cudaEventSynchronize(bw->uploaded[q]));   // the stage buffer's last upload has left it
+    for (uint32_t p = 0; p < cnt; p++) {
+      Fr* dst = bw->w_stage[q] + (size_t)p * ws;
+      memcpy(dst, inputs[lo + p], (size_t)pk->n_in * sizeof(Fr));
+      if (pk->n_aux) memcpy(dst + pk->n_in, aux[lo + p], (size_t)pk->n_aux * sizeof(Fr));
+    }
+    // the witness array is read by the previous chunk's MSMs on the side streams
+    if (k > 0)
+      for (int e = 1; e <= 4; e++) FB_CUDA(cudaStreamWaitEvent(st, bw->done[q ^ 1][e], 0));
+    FB_CUDA(cudaMemcpyAsync(bw->w, bw->w_stage[q], (size_t)cnt * ws * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaEventRecord(bw->uploaded[q], st));
+    bw->used[q] = true;
+    FB_CUDA(cudaEventRecord(bw->start, st));
+    for (int i = 0; i < 3; i++) FB_CUDA(cudaStreamWaitEvent(ctx->aux[i], bw->start, 0));
+    const MsmPlan ph = pk->plan_h.batched(cnt, m), pl = pk->plan_l.batched(cnt, ws), pa = pk->plan_a.batched(cnt, ws),
+                  pb = pk->plan_b.batched(cnt, ws);
+    auto fetch = [&](int slot, size_t bytes, cudaStream_t sx) -> cudaError_t {
+      cudaError_t e = cudaMemcpyAsync(hslot(q, slot), dslot(slot), bytes, cudaMemcpyDeviceToHost, sx);
+      if (e == cudaSuccess) e = cudaEventRecord(bw->done[q][slot], sx);
+      return e;
+    };
+    int rc = msm_g2(pk->b2, bw->w, pk->b_map, pb, bw->msm[3], dslot(4), false, sB);
+    if (!rc) FB_CUDA(fetch(4, sizeof(G2XYZZ) * pb.vbits(), sB));
+    if (!rc) rc = msm_g1(pk->b1, bw->w, pk->b_map, pb, bw->msm[3], (G1XYZZ*)dslot(3), true, sB);
+    if (!rc) FB_CUDA(fetch(3, sizeof(G1XYZZ) * pb.vbits(), sB));
+    if (!rc) rc = msm_g1(pk->a, bw->w, pk->a_map, pa, bw->msm[2], (G1XYZZ*)dslot(2), false, sA);
+    if (!rc) FB_CUDA(fetch(2, sizeof(G1XYZZ) * pa.vbits(), sA));
+    if (!rc) rc = msm_g1(pk->l, bw->w + pk->n_in, nullptr, pl, bw->msm[1], (G1XYZZ*)dslot(1), false, sL);
+    if (!rc) FB_CUDA(fetch(1, sizeof(G1XYZZ) * pl.vbits(), sL));
+    if (rc) { set_error("batched MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
+    rc = eval_r1cs_batch(pk->csr, bw->w, ws, pk->n_in, bw->ev[0], bw->ev[1], bw->ev[2], m, cnt, st);
+    if (rc) return rc;
+    for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(bw->ev[i], st, cnt, m);
+    pk->dom.pointwise_then_icoset_fft(bw->ev[0], bw->ev[1], bw->ev[2], st, cnt, m);
+    rc = msm_g1(pk->h, bw->ev[0], nullptr, ph, bw->msm[0], (G1XYZZ*)dslot(0), false, st);
+    if (rc) { set_error("batched MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
+    FB_CUDA(fetch(0, sizeof(G1XYZZ) * ph.vbits(), st));
+    return FB_OK;
+  };
+
+  auto tails = [&](uint32_t k) -> int {
+    const int q = (int)(k & 1);
+    const uint32_t lo = k * P, cnt = std::min(P, count - lo);
+    for (int e = 0; e < 5; e++) FB_CUDA(cudaEventSynchronize(bw->done[q][e]));
+    const int vh = pk->plan_h.vbits_per_set(), vl = pk->plan_l.vbits_per_set(), va = pk->plan_a.vbits_per_set(),
+              vb = pk->plan_b.vbits_per_set();
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> err{FB_OK};
+    std::string err_msg;
+    std::mutex err_mu;
+    auto work = [&] {
+      for (;;) {
+        const uint32_t p = next.fetch_add(1);
+        if (p >= cnt) return;
+        const H2 B2 = msm_horner_host<HFq2>(hslot(q, 4) + (size_t)p * vb, vb);
+        const H1 B1 = msm_horner_host<HFq>((const G1XYZZ*)hslot(q, 3) + (size_t)p * vb, vb);
+        const H1 A = msm_horner_host<HFq>((const G1XYZZ*)hslot(q, 2) + (size_t)p * va, va);
+        const H1 L = msm_horner_host<HFq>((const G1XYZZ*)hslot(q, 1) + (size_t)p * vl, vl);
+        const H1 H = msm_horner_host<HFq>((const G1XYZZ*)hslot(q, 0) + (size_t)p * vh, vh);
+        FixedTerms ft;
+        const int frc = fixed_terms(&vk, kt, r + 4 * (size_t)(lo + p), s + 4 * (size_t)(lo + p), ft);
+        if (frc) {
+          std::lock_guard<std::mutex> lk(err_mu);
+          err = frc;
+          err_msg = last_error_cstr();
+          return;
+        }
+        finish_proof(ft, H, L, A, B1, B2, nullptr, nullptr, proofs_raw + 256 * (size_t)(lo + p));
+      }
+    };
+    const int T = std::min<int>(host_threads, (int)cnt);
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+    if (err) { set_error("%s", err_msg.c_str()); return err; }
+    return FB_OK;
+  };
+
+  int rc = FB_OK;
+  for (uint32_t k = 0; k < nchunks && !rc; k++) {
+    rc = enqueue(k);
+    if (!rc && k > 0) rc = tails(k - 1);
+  }
+  if (!rc) rc = tails(nchunks - 1);
+  if (rc) cudaDeviceSynchronize();
+  FB_CUDA(cudaGetLastError());
+  return rc;
+}
+}  // namespace fb
+
+extern "C" {
+
 int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
                    const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
                    uint8_t* proofs_raw) {
@@ -1120,6 +1319,18 @@ int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* cons
   ProvingKey* pk = reinterpret_cast<ProvingKey*>(pk_);
   Ctx* c0 = reinterpret_cast<Ctx*>(ctx);
   if (!pk || !c0) { set_error("fb_prove_batch: null handle"); return FB_ERR_ARG; }
+  if (n_in != pk->n_in || n_aux != pk->n_aux) {
+    set_error("witness has n_in=%u n_aux=%u, key expects %u / %u", n_in, n_aux, pk->n_in, pk->n_aux);
+    return FB_ERR_ARG;
+  }
+  if (c0 != pk->ctx) { set_error("fb_prove_batch: the key was loaded on a different fb_ctx"); return FB_ERR_ARG; }
+  // small keys: one set of launches per chunk of proofs (prove_batched); FB_BATCH_MODE=slots keeps the older
+  // scheme below (independent proves in flight on their own streams, CUDA-graph replay)
+  {
+    const char* mode = getenv("FB_BATCH_MODE");
+    if (count >= 2 && pk->m <= (1u << 16) && pk->nshards == 1 && !pk->dist_g && !g_serial && !(mode && !strcmp(mode, "slots")))
+      return prove_batched(c0, pk, count, inputs, aux, r, s, proofs_raw);
+  }
   int want = 8;
   if (const char* e = getenv("FB_BATCH_SLOTS")) want = std::max(1, std::min(32, atoi(e)));
   // big keys saturate the GPU on their own (and their workspaces are large); sharded keys prove collectively

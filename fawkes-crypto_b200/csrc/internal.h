@@ -27,7 +27,7 @@ extern int g_msm_batch_affine;
 // ---- instrumentation (bench.py: gpu_launches and the live roofline timing) -------------
 extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
-enum { KSTAT_ACC_G1 = 0, KSTAT_ACC_G2 = 1, KSTAT_NTT = 2, KSTAT_KINDS = 3 };
+enum { KSTAT_ACC_G1 = 0, KSTAT_ACC_G2 = 1, KSTAT_NTT = 2, KSTAT_EXCHANGE = 3, KSTAT_SORT = 4, KSTAT_REDUCE = 5, KSTAT_KINDS = 6 };
 void kstat_begin(int kind, cudaStream_t st);    // no-ops unless enabled
 void kstat_end(int kind, cudaStream_t st);
 #define FB_CUDA(call)                                                              \
@@ -113,6 +113,7 @@ struct ProvingKey {
   // window tables, CSR, twiddles, host tables) and own everything a prove writes, each with its own streams
   bool is_slot = false;
   std::vector<ProvingKey*> slots;
+  void* batch = nullptr;  // BatchWork* (api.cu): workspaces of the batched path of fb_prove_batch
   // small keys: the whole device side of a prove (upload, ~70 kernels on four streams, result copies)
   // captured once as a CUDA graph and replayed per proof (api.cu: prove_graph)
   cudaGraphExec_t graph_exec = nullptr;
@@ -164,6 +165,8 @@ void dist_destroy(Ctx* ctx);  // communicator + buffers (fb_shutdown)
 // prove.cu
 int eval_r1cs(const DevCsr& csr, const Fr* w, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,
               cudaStream_t st);
+int eval_r1cs_batch(const DevCsr& csr, const Fr* w, uint64_t wstride, uint32_t n_in, Fr* a, Fr* b, Fr* c, uint64_t m,
+                    uint32_t count, cudaStream_t st);
 int eval_r1cs_cyclic(const DevCsr& local_csr, const Fr* w, uint32_t n_in, uint32_t n_gates_global, int g, int rank,
                      Fr* a, Fr* b, Fr* c, uint64_t ml, cudaStream_t st);
 

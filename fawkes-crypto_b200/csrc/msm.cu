@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 namespace fb {
 
@@ -58,6 +59,18 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   return p;
 }
 
+MsmPlan MsmPlan::batched(uint32_t nsets, uint64_t stride) const {
+  MsmPlan p = *this;
+  p.sets = nsets;
+  p.sstride = stride;
+  p.batched_out = true;
+  uint64_t want = p.entries() >> 18;
+  int tl = 4;
+  while (tl < 8 && (1ull << tl) < want) tl++;
+  p.task_log = tl;
+  return p;
+}
+
 // segments one k_segment_bits CTA folds (per (window, bit) job the segment range is cut into parts)
 constexpr int MSM_BITS_PART_LOG = 11;
 static inline int bits_parts(const MsmPlan& p) {
@@ -71,11 +84,11 @@ int MsmScratch::alloc(const MsmPlan* plans, int count, bool need_g2) {
   for (int i = 0; i < count; i++) {
     const MsmPlan& p = plans[i];
     if (p.n == 0) continue;
-    ent = std::max<uint64_t>(ent, (uint64_t)p.n * p.W);
+    ent = std::max<uint64_t>(ent, p.entries());
     bk = std::max<uint64_t>(bk, p.nbuckets());
-    tk = std::max<uint64_t>(tk, (((uint64_t)p.n * p.W) >> p.task_log) + p.nbuckets() + 2);
+    tk = std::max<uint64_t>(tk, (p.entries() >> p.task_log) + p.nbuckets() + 2);
     // the XYZZ pass after the batch-affine rounds runs short tasks over the reduced list
-    tk = std::max<uint64_t>(tk, (((((uint64_t)p.n * p.W) >> p.ba_rounds()) + p.nbuckets() + 1) >> MSM_MIN_TASK_LOG) +
+    tk = std::max<uint64_t>(tk, ((((p.entries()) >> p.ba_rounds()) + p.nbuckets() + 1) >> MSM_MIN_TASK_LOG) +
                                     p.nbuckets() + 2);
     vp = std::max<uint64_t>(vp, (uint64_t)p.wred() * (p.c - p.seg_log) * bits_parts(p));
   }
@@ -106,7 +119,7 @@ int MsmScratch::alloc_batch_affine(const MsmPlan* plans, int count, bool need_g2
   uint64_t ent = 0, bk = 1;
   for (int i = 0; i < count; i++) {
     if (plans[i].n == 0 || plans[i].ba_rounds() == 0) continue;
-    ent = std::max<uint64_t>(ent, (uint64_t)plans[i].n * plans[i].W);
+    ent = std::max<uint64_t>(ent, plans[i].entries());
     bk = std::max<uint64_t>(bk, plans[i].nbuckets());
   }
   if (ent == 0) return 0;
@@ -152,10 +165,13 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t* s, int pos, int 
 // SCATTER=false: histogram.  SCATTER=true: place entries using cursor (pre-loaded with offsets).
 template <bool SCATTER>
 __global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restrict__ map,
-                         uint32_t n, int c, int W, uint32_t B, bool table, uint32_t* __restrict__ counter,
-                         uint32_t* __restrict__ sorted) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    Fr s = from_mont(scalars[map ? map[i] : i]);
+                         uint32_t n, int c, int W, uint32_t B, bool table, uint32_t sets, uint64_t sstride,
+                         uint32_t* __restrict__ counter, uint32_t* __restrict__ sorted) {
+  const uint64_t total = (uint64_t)n * sets;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t set = sets == 1 ? 0u : (uint32_t)(j / n);
+    const uint32_t i = (uint32_t)(j - (uint64_t)set * n);
+    Fr s = from_mont(scalars[set * sstride + (map ? map[i] : i)]);
     uint32_t carry = 0;
     for (int w = 0; w < W; w++) {
       uint32_t v = window_bits(s.v, w * c, c) + carry;
@@ -169,7 +185,7 @@ __global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restr
       }
       if (mag != 0) {
         // table mode: every window shares one bucket set and digit w selects the point 2^(c w) P_i
-        uint32_t bucket = (table ? 0u : (uint32_t)w * B) + mag - 1;
+        uint32_t bucket = (table ? set : set * (uint32_t)W + (uint32_t)w) * B + mag - 1;
         uint32_t pos = atomicAdd(&counter[bucket], 1u);
         if (SCATTER) sorted[pos] = (table ? (uint32_t)w * n + i : i) | (neg << 31);
       }
@@ -178,8 +194,7 @@ __global__ void k_digits(const Fr* __restrict__ scalars, const uint32_t* __restr
 }
 
 // ------------------------------------------------------------------ scan ---
-__global__ void k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                             uint32_t* __restrict__ blocksums, uint32_t n) {
+__global__ void k_scan_block(const uint32_t* in, uint32_t* out, uint32_t* __restrict__ blocksums, uint32_t n) {
   __shared__ uint32_t wsum[32];
   const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
   uint32_t v = i < n ? in[i] : 0;
@@ -742,26 +757,34 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
                    cudaStream_t st) {
   const uint32_t nb = p.nbuckets();
   if (p.W > MSM_MAX_W || bits_parts(p) > 1024) return -1;
+  const size_t vcount = p.batched_out ? (size_t)p.vbits() : (size_t)MSM_VBITS;
   if (p.n == 0) {
-    cudaMemsetAsync(out, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
+    cudaMemsetAsync(out, 0, sizeof(XYZZ<F>) * vcount, st);
     return 0;
   }
-  if ((uint64_t)p.n * p.W > s.cap_entries || nb > s.cap_buckets) return -2;
+  if (p.entries() > s.cap_entries || nb > s.cap_buckets) return -2;
   if (!reuse_sort) {
+    kstat_begin(KSTAT_SORT, st);
+    // Counting sort on global atomics.  A two-pass LSD radix sort with warp-private shared-memory cursors was built
+    // and measured this round (profiles/r02_radix_sort_experiment.txt): its count passes ran in 0.3-0.75 ms at 2^24, but its
+    // scatter passes took 7 and 13 ms -- 2368 warps x 1024 bins of open 4/8-byte write streams (78 MB of partial
+    // sectors next to a 1.75 GB stream) thrash L2 into read-modify-writes, 90 ms per prove against 18.6 ms here.
+    // Beating this path needs tiles sorted in shared memory and written out as full sectors.
     cudaMemsetAsync(s.hist, 0, (size_t)(nb + 1) * 4, st);
-    const unsigned dg = (unsigned)std::min<uint64_t>((p.n + 255) / 256, 148 * 16);
-    k_digits<false><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, s.hist, nullptr);
+    const unsigned dg = (unsigned)std::min<uint64_t>(((uint64_t)p.n * p.sets + 255) / 256, 148 * 16);
+    k_digits<false><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, p.sets, p.sstride, s.hist, nullptr);
     const unsigned sb = (nb + 1 + 1023) / 1024;
     k_scan_block<<<sb, 1024, 0, st>>>(s.hist, s.offsets, s.blocksums, nb + 1);
     k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb);
     k_scan_add<<<sb, 1024, 0, st>>>(s.offsets, s.cursor, s.blocksums, nb + 1);
-    k_digits<true><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, s.cursor, s.sorted);
+    k_digits<true><<<dg, 256, 0, st>>>(scalars, map, p.n, p.c, p.W, p.B, p.table, p.sets, p.sstride, s.cursor, s.sorted);
+    kstat_end(KSTAT_SORT, st);
   }
   XYZZ<F>* buckets = reinterpret_cast<XYZZ<F>*>(s.buckets);
   XYZZ<F>* segR = reinterpret_cast<XYZZ<F>*>(s.segR);
   XYZZ<F>* segS = reinterpret_cast<XYZZ<F>*>(s.segS);
   XYZZ<F>* partials = reinterpret_cast<XYZZ<F>*>(s.partials);
-  const uint64_t N = (uint64_t)p.n * p.W;
+  const uint64_t N = p.entries();
   const int kind = sizeof(F) == sizeof(Fq) ? KSTAT_ACC_G1 : KSTAT_ACC_G2;
   // ---- batch-affine rounds: sorted entries -> ~N / 2^R affine points, still grouped by bucket
   // mode 3: G2 only (an Fq2 add is 2.5x the MACs of an Fq one for 2x the bytes, so the rounds pay there first)
@@ -823,15 +846,16 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
                                                                                  p.task_log, partials, msm_ld64());
   kstat_end(kind, st);
   count_launch(reuse_sort ? 5 : 10);
+  kstat_begin(KSTAT_REDUCE, st);
   k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, offsets, nb, task_log, buckets, s.heavy);
   k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, offsets, task_log, s.heavy, buckets);
   const int sbits = p.c - 1 - p.seg_log;  // bits of the segment index within a window
   const uint32_t nsegs = nb >> p.seg_log;
-  XYZZ<F>* V = out;  // MSM_VBITS entries
+  XYZZ<F>* V = out;  // MSM_VBITS entries (vbits() for a batched plan)
   constexpr int BT = sizeof(F) == sizeof(Fq) ? 256 : 128;
   const int parts = bits_parts(p);
   const int jobs = p.wred() * (1 + sbits);
-  cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * MSM_VBITS, st);
+  cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * vcount, st);
   k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
   k_segment_bits<F, BT><<<jobs * parts, BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, parts, V,
                                                     reinterpret_cast<XYZZ<F>*>(s.winsum));
@@ -839,6 +863,7 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
     k_fold_parts<F><<<jobs, 32, 0, st>>>(reinterpret_cast<XYZZ<F>*>(s.winsum), p.c, p.seg_log, sbits, parts, V);
     count_launch(1);
   }
+  kstat_end(KSTAT_REDUCE, st);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

@@ -47,8 +47,17 @@ struct MsmPlan {
   // bucket set.  The reduction then costs 2^(c-1) buckets instead of W * 2^(c-1), which lets c grow by
   // ~4 bits: 15 -> 12 digits per scalar at n = 2^24.  Costs W x the base memory (HBM is 180 GB).
   bool table = false;
+  // Batched MSM (fb_prove_batch on a small key): `sets` independent scalar vectors over the SAME bases, set p
+  // reading scalars[p * sstride + ...]; every set gets its own buckets (bucket id = set * B + digit - 1), so one
+  // sort, one accumulation and one reduction carry the digits of all the proofs of a batch.
+  uint32_t sets = 1;
+  uint64_t sstride = 0;
+  bool batched_out = false;  // result array holds vbits() entries (set p at p * vbits_per_set()), not MSM_VBITS
   static MsmPlan make(uint32_t n, bool table = false);
-  int wred() const { return table ? 1 : W; }                   // bucket sets to reduce
+  MsmPlan batched(uint32_t nsets, uint64_t stride) const;      // same window, task size for the whole batch
+  uint64_t entries() const { return (uint64_t)n * W * sets; }  // digits to sort and accumulate (upper bound)
+  int wred() const { return (int)sets * (table ? 1 : W); }     // bucket sets to reduce
+  int vbits_per_set() const { return (table ? 1 : W) * c; }    // V entries of one scalar vector
   uint32_t nbuckets() const { return (uint32_t)wred() * B; }
   uint32_t nsegs() const { return nbuckets() >> seg_log; }
   int vbits() const { return wred() * c; }                     // V entries the host Horner consumes
@@ -93,7 +102,8 @@ struct MsmScratch {
 };
 
 // scalars: Montgomery Fr, addressed as scalars[map ? map[i] : i]; bases: affine Montgomery.
-// result: out[MSM_VBITS] on device, the per-bit sums V[p] with  MSM = sum_p 2^p V[p]  (finish with
+// result: out[MSM_VBITS] on device (out[plan.vbits()] for a batched plan, set p at out + p * vbits_per_set()),
+// the per-bit sums V[p] with  MSM = sum_p 2^p V[p]  (finish with
 // msm_horner_host after copying them to the host).  Steps 1-3 are skipped when reuse_sort is set
 // (same scalars as the previous call on this scratch: B_g2 then B_g1).
 int msm_g1(const G1Affine* bases, const Fr* scalars, const uint32_t* map, const MsmPlan& plan,

@@ -161,8 +161,11 @@ __device__ __forceinline__ void dit_stages(const Tile& s, const Fr* tab, int k, 
 template <int MODE, bool NEG0>
 __global__ void __launch_bounds__(NTT_THREADS)
 k_ntt_pass(Fr* x, const Fr* y, const Fr* z, const Fr* tab0, const Fr* tab1, int k, int lb, int a,
-           int b, Fr k1, Fr k2, NttShard sh) {
+           int b, Fr k1, Fr k2, NttShard sh, uint64_t bstride) {
   extern __shared__ uint4 smem[];
+  // batched transforms (fb_prove_batch): blockIdx.y selects one of gridDim.y arrays, bstride elements apart
+  x += (uint64_t)blockIdx.y * bstride;
+  if (MODE == 3) { y += (uint64_t)blockIdx.y * bstride; z += (uint64_t)blockIdx.y * bstride; }
   Tile s{smem, smem + (1 << (a + b))};
   const int tile = 1 << (a + b);
   // block -> (hi, lo chunk)
@@ -290,41 +293,44 @@ void NttDomain::destroy() {
 template <int MODE, bool NEG0>
 static void launch_pass(Fr* x, const Fr* y, const Fr* z, const Fr* t0, const Fr* t1, int k, int lb,
                         int b, const Fr& k1, const Fr& k2, cudaStream_t st, int kl = -1,
-                        NttShard sh = NttShard{0, 0}) {
+                        NttShard sh = NttShard{0, 0}, unsigned batch = 1, uint64_t bstride = 0) {
   if (kl < 0) kl = k;
   int a = std::min(lb, NTT_LOG_TILE - b);
   size_t sm = (size_t)sizeof(Fr) << (a + b);
   unsigned blocks = 1u << (kl - a - b);
   kstat_begin(KSTAT_NTT, st);
-  k_ntt_pass<MODE, NEG0><<<blocks, NTT_THREADS, sm, st>>>(x, y, z, t0, t1, k, lb, a, b, k1, k2, sh);
+  k_ntt_pass<MODE, NEG0><<<dim3(blocks, batch), NTT_THREADS, sm, st>>>(x, y, z, t0, t1, k, lb, a, b, k1, k2, sh, bstride);
   kstat_end(KSTAT_NTT, st);
   count_launch();
 }
 
 // x (natural order evaluations on H) -> natural order evaluations on gH, both scaled by m
-void NttDomain::ifft_then_coset_fft(Fr* x, cudaStream_t st) const {
+void NttDomain::ifft_then_coset_fft(Fr* x, cudaStream_t st, unsigned batch, uint64_t bstride) const {
   Fr z = Fr::zero();
+  const NttShard one{0, 0};
   for (int i = n_strided - 1; i >= 0; i--)
-    launch_pass<0, true>(x, nullptr, nullptr, tab_plain, nullptr, k, pass_lb[i], pass_b[i], z, z, st);
-  launch_pass<2, true>(x, nullptr, nullptr, tab_plain, tab_coset, k, 0, plan_bm, z, z, st);
+    launch_pass<0, true>(x, nullptr, nullptr, tab_plain, nullptr, k, pass_lb[i], pass_b[i], z, z, st, -1, one, batch, bstride);
+  launch_pass<2, true>(x, nullptr, nullptr, tab_plain, tab_coset, k, 0, plan_bm, z, z, st, -1, one, batch, bstride);
   for (int i = 0; i < n_strided; i++)
-    launch_pass<1, false>(x, nullptr, nullptr, tab_coset, nullptr, k, pass_lb[i], pass_b[i], z, z, st);
+    launch_pass<1, false>(x, nullptr, nullptr, tab_coset, nullptr, k, pass_lb[i], pass_b[i], z, z, st, -1, one, batch, bstride);
 }
 
 // a <- icoset_fft((a*b - c)/Z) in BIT-REVERSED coefficient order, exact (1/m folded)
-void NttDomain::pointwise_then_icoset_fft(Fr* a, const Fr* b, const Fr* c, cudaStream_t st) const {
+void NttDomain::pointwise_then_icoset_fft(Fr* a, const Fr* b, const Fr* c, cudaStream_t st, unsigned batch,
+                                          uint64_t bstride) const {
   Fr z = Fr::zero();
+  const NttShard one{0, 0};
   if (n_strided == 0) {
-    launch_pass<3, false>(a, b, c, tab_icoset, nullptr, k, 0, plan_bm, k1, k2, st);
+    launch_pass<3, false>(a, b, c, tab_icoset, nullptr, k, 0, plan_bm, k1, k2, st, -1, one, batch, bstride);
     return;
   }
   for (int i = n_strided - 1; i >= 0; i--) {
     if (i == n_strided - 1)
-      launch_pass<3, false>(a, b, c, tab_icoset, nullptr, k, pass_lb[i], pass_b[i], k1, k2, st);
+      launch_pass<3, false>(a, b, c, tab_icoset, nullptr, k, pass_lb[i], pass_b[i], k1, k2, st, -1, one, batch, bstride);
     else
-      launch_pass<0, false>(a, nullptr, nullptr, tab_icoset, nullptr, k, pass_lb[i], pass_b[i], z, z, st);
+      launch_pass<0, false>(a, nullptr, nullptr, tab_icoset, nullptr, k, pass_lb[i], pass_b[i], z, z, st, -1, one, batch, bstride);
   }
-  launch_pass<0, false>(a, nullptr, nullptr, tab_icoset, nullptr, k, 0, plan_bm, z, z, st);
+  launch_pass<0, false>(a, nullptr, nullptr, tab_icoset, nullptr, k, 0, plan_bm, z, z, st, -1, one, batch, bstride);
 }
 
 // Stand-alone transforms for tests / setup.  Natural order in and out.
@@ -417,17 +423,21 @@ int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int ran
       launch_pass<0, true>(ev[v], nullptr, nullptr, tab_plain, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
   // 2. cyclic -> block: contiguous chunks out, strided placement in
   const Fr* send3[3] = {ev[0], ev[1], ev[2]};
+  kstat_begin(KSTAT_EXCHANGE, st);
   int rc = xch->all_to_all(send3, tmp, 3, C, st);
   if (rc) return rc;
   for (int v = 0; v < 3; v++) k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[v], tmp[v], g, C);
+  kstat_end(KSTAT_EXCHANGE, st);
   // 3. block layout: last bm inverse stages + first bm forward (coset) stages in one tile
   for (int v = 0; v < 3; v++)
     launch_pass<2, true>(ev[v], nullptr, nullptr, tab_plain, tab_coset, k, 0, bm, z, z, st, kl, blk);
   // 4. block -> cyclic
+  kstat_begin(KSTAT_EXCHANGE, st);
   for (int v = 0; v < 3; v++) k_pack_from_block<<<grid_for(ml), 256, 0, st>>>(tmp[v], ev[v], g, C);
   const Fr* send3b[3] = {tmp[0], tmp[1], tmp[2]};
   rc = xch->all_to_all(send3b, ev, 3, C, st);
   if (rc) return rc;
+  kstat_end(KSTAT_EXCHANGE, st);
   // 5. cyclic forward (coset) DIT on the high bits
   for (int v = 0; v < 3; v++)
     for (int i = 0; i < np; i++)
@@ -442,9 +452,11 @@ int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int ran
   // 7. cyclic -> block, then the low bm stages: H in bit-reversed order, block layout
   const Fr* send1[1] = {ev[0]};
   Fr* recv1[1] = {tmp[0]};
+  kstat_begin(KSTAT_EXCHANGE, st);
   rc = xch->all_to_all(send1, recv1, 1, C, st);
   if (rc) return rc;
   k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[0], tmp[0], g, C);
+  kstat_end(KSTAT_EXCHANGE, st);
   launch_pass<0, false>(ev[0], nullptr, nullptr, tab_icoset, nullptr, k, 0, bm, z, z, st, kl, blk);
   count_launch(10);
   return cudaGetLastError() == cudaSuccess ? 0 : -3;

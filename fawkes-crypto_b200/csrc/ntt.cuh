@@ -35,8 +35,10 @@ struct NttDomain {
 
   int init(int k, cudaStream_t st);
   void destroy();
-  void ifft_then_coset_fft(Fr* x, cudaStream_t st) const;
-  void pointwise_then_icoset_fft(Fr* a, const Fr* b, const Fr* c, cudaStream_t st) const;
+  // batch > 1: the same transform on `batch` arrays, bstride elements apart (fb_prove_batch)
+  void ifft_then_coset_fft(Fr* x, cudaStream_t st, unsigned batch = 1, uint64_t bstride = 0) const;
+  void pointwise_then_icoset_fft(Fr* a, const Fr* b, const Fr* c, cudaStream_t st, unsigned batch = 1,
+                                 uint64_t bstride = 0) const;
   void transform(Fr* x, Fr* scratch, int kind, cudaStream_t st) const;
   void bitrev(Fr* dst, const Fr* src, cudaStream_t st) const;
   // distributed H pipeline over G = 2^g ranks (see ntt.cu); ev/tmp are local arrays of 2^(k-g)

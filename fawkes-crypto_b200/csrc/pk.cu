@@ -38,8 +38,8 @@ struct KStat {
   std::vector<cudaEvent_t> pool;
   struct Rec { int kind; cudaEvent_t a, b; };
   std::vector<Rec> open_recs, recs;
-  unsigned long long count[KSTAT_KINDS] = {0, 0, 0};
-  double ms[KSTAT_KINDS] = {0, 0, 0};
+  unsigned long long count[KSTAT_KINDS] = {};
+  double ms[KSTAT_KINDS] = {};
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e;

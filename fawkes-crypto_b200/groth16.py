@@ -372,11 +372,21 @@ class Parameters:
 
 # ------------------------------------------------------------ entry points ---
 def _sample_fr() -> int:
-    """OsRng-style rejection sampling (osrng.rs:12-18; shave 2 bits, reject >= r)."""
+    """One uniformly random Fr, drawn the way the reference draws r and s (prover.rs:78-80): `OsRng::next_u32` is 4
+    bytes of OS randomness read BIG-endian (osrng.rs:12-18), `next_u64` is rand 0.4's default (two next_u32, high
+    word first), ff_ce's `Rand for Fr` fills the 4 limbs in order, clears the top REPR_SHAVE_BITS = 2 bits of the
+    top limb, rejects values >= r and takes the limbs AS the Montgomery representation.  Returned as the canonical
+    integer of that Montgomery value (rust/fawkes-b200/src/osrng.rs is the same routine for the Rust shim)."""
     while True:
-        v = int.from_bytes(os.urandom(32), "little") & ((1 << 254) - 1)
+        limbs = []
+        for _ in range(4):
+            hi = int.from_bytes(os.urandom(4), "big")
+            lo = int.from_bytes(os.urandom(4), "big")
+            limbs.append((hi << 32) | lo)
+        limbs[3] &= (1 << 62) - 1
+        v = sum(l << (64 * i) for i, l in enumerate(limbs))
         if v < FR_MOD:
-            return v
+            return _from_mont(v, FR_MOD)
 
 
 def setup(circuit: Circuit, ctx: Context, trapdoor: Optional[Sequence[int]] = None, num_gates: Optional[int] = None,

@@ -195,7 +195,8 @@ int fb_circuit_csr(const fb_circuit* c, int m, const uint32_t** rowptr, const ui
                    const uint32_t** cidx, uint64_t* nnz, const uint64_t** coef_table, uint64_t* ncoef);
 /* instrumentation: kernels launched by the library so far; CUDA-event timing of the dominant
  * kernels on their launching stream (which: 0 G1 bucket accumulation, 1 G2 bucket
- * accumulation, 2 NTT passes) */
+ * accumulation, 2 NTT passes, 3 NTT exchanges of a distributed key incl. pack/unpack, 4 digit sorts,
+ * 5 bucket reductions) */
 uint64_t fb_launch_count(void);
 /* 1: run every kernel of a prove on one stream (per-kernel timings are then undisturbed);
  * 0 (default): the witness-only MSMs run on side streams beside the H pipeline */

@@ -38,8 +38,13 @@ def _worker(rank, world, port, q):
     tdi = [fb.groth16.fr_unraw(x) for x in td]
     params = fb.setup(circ, ctx, trapdoor=tdi[:5])
     wi, wa = circ.witness()
+    # the key of this rank comes from the SHARDED setup (fb_setup_shard: only this rank's points are generated, the
+    # rest of the byte string is points at infinity); the full setup above is kept for the single-GPU reference
+    params_sh = fb.setup(circ, ctx, trapdoor=tdi[:5], shard=rank, nshards=world)
+    assert len(params_sh.bellman_bytes) == len(params.bellman_bytes)
+    assert bytes(params_sh.bellman_bytes[:580]) == bytes(params.bellman_bytes[:580])      # same verifying key
     pk = C.c_void_p()
-    pb = params.bellman_bytes
+    pb = params_sh.bellman_bytes
     fb.native.check(lib.fb_pk_load_shard(ctx.handle, fb.native.ptr(pb), len(pb), circ.handle, 1, rank, world, C.byref(pk)))
     # library-side collective prove: every rank calls fb_prove on its shard of the key; the 640-byte partial sums
     # travel over the library's own NCCL communicator and EVERY rank returns the proof

@@ -251,8 +251,11 @@ def test_sharded_prove_equals_unsharded(ctx, nshards):
     _, ref = fb.groth16.prove_with_rs(params, wi, wa, td[5], td[6], ctx)
     params.unload()
     parts = np.zeros((nshards, 640), dtype=np.uint8)
-    pb = params.bellman_bytes
     for sh in range(nshards):
+        # every other shard loads its key from the sharded setup (fb_setup_shard: only this shard's query points are
+        # generated, everything else is the point at infinity), the rest from the full Parameters
+        pb = params.bellman_bytes if sh % 2 else fb.setup(circ, ctx, trapdoor=td[:5], shard=sh, nshards=nshards).bellman_bytes
+        assert len(pb) == len(params.bellman_bytes)
         pk = C.c_void_p()
         fb.native.check(fb.native.lib.fb_pk_load_shard(ctx.handle, fb.native.ptr(pb), len(pb), circ.handle, 1, sh,
                                                        nshards, C.byref(pk)))
@@ -261,6 +264,7 @@ def test_sharded_prove_equals_unsharded(ctx, nshards):
         fb.native.lib.fb_pk_free(pk)
     r, s = fr_np([td[5]])[0], fr_np([td[6]])[0]
     out = np.zeros(256, dtype=np.uint8)
+    pb = params.bellman_bytes
     fb.native.check(fb.native.lib.fb_prove_finish(fb.native.ptr(pb), len(pb), parts.ctypes.data, nshards,
                                                   r.ctypes.data, s.ctypes.data, out.ctypes.data))
     assert out.tobytes() == ref.to_raw()
@@ -293,31 +297,65 @@ def test_witness_with_zeros_and_ones(ctx):
     params.unload()
 
 
-def test_prove_batch_matches_single_proofs(ctx):
-    """fb_prove_batch (configs[1] shape: many proofs on one resident key) == proof-by-proof."""
+@pytest.mark.parametrize("mode,chunk,tables", [("batched", 64, 1), ("batched", 3, 1), ("batched", 2, 0), ("slots", 0, 1)])
+def test_prove_batch_matches_single_proofs(ctx, mode, chunk, tables):
+    """fb_prove_batch (configs[1] shape: many proofs on one resident key) == the oracle's proof of each witness.
+    batched = one set of launches per chunk of proofs, buckets keyed by (proof, digit) -- with chunks that divide
+    the batch, chunks with a remainder, and without window tables (bucket sets per (proof, window)); slots = the
+    older scheme (independent proves in flight).  DIFFERENT witnesses per proof: a second circuit input changes
+    every aux value downstream of it."""
     import ctypes as C
+    import os
     import fawkes_crypto_b200 as fb
     seed = synth.SEED_BASE + 5000
-    n_rows, count = 500, 5
+    n_rows, count = 500, 7
     gates, inp, aux = synth.synth_circuit(n_rows, seed)
     td, r0, s0 = synth.synth_trapdoor(seed)
     P = og.setup(gates, 2, len(aux), td)
     raw = b"".join(codec.gate_borsh(g) for g in gates)
-    params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
-    pk = params.load(ctx)
-    # the same satisfying witness with different blinding per proof
-    rs = [((r0 + 7 * i) % bn.R, (s0 + 11 * i) % bn.R) for i in range(count)]
-    wi, wa = fr_np(inp), fr_np(aux)
-    ins = (C.c_void_p * count)(*[wi.ctypes.data] * count)
-    axs = (C.c_void_p * count)(*[wa.ctypes.data] * count)
-    ra, sa = fr_np([x for x, _ in rs]), fr_np([y for _, y in rs])
-    out = np.zeros((count, 256), dtype=np.uint8)
-    fb.native.check(fb.native.lib.fb_prove_batch(ctx.handle, pk, count, ins, 2, axs, len(aux), ra.ctypes.data,
-                                                 sa.ctypes.data, out.ctypes.data))
-    for i, (r, s) in enumerate(rs):
-        ref = og.prove(P, gates, inp, aux, r, s)
-        assert out[i].tobytes() == codec.proof_raw(ref), i
-    params.unload()
+    # witnesses: re-evaluate the circuit from different initial aux values (rows 1.. define aux[16..] as products)
+    wits = []
+    for i in range(count):
+        a = list(aux[:synth.N_INIT_AUX])
+        a[3] = (a[3] + 1000 * i) % bn.R
+        ins_i = [1, a[0]]
+        for g in gates[1:]:
+            val = lambda t: ins_i[t[1]] if t[0] == og.INPUT else a[t[1]]
+            ea = sum(c * val(t) for c, t in g[0]) % bn.R
+            eb = sum(c * val(t) for c, t in g[1]) % bn.R
+            a.append(ea * eb % bn.R)
+        wits.append((ins_i, a))
+    assert wits[0][1] == aux and wits[1][1] != aux
+    fb.native.lib.fb_set_msm_tables(tables)
+    os.environ["FB_BATCH_MODE"] = mode
+    if chunk:
+        os.environ["FB_BATCH_P"] = str(chunk)
+    try:
+        params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
+        pk = params.load(ctx)
+        rs = [((r0 + 7 * i) % bn.R, (s0 + 11 * i) % bn.R) for i in range(count)]
+        wis = [fr_np(w[0]) for w in wits]
+        was = [fr_np(w[1]) for w in wits]
+        ins = (C.c_void_p * count)(*[x.ctypes.data for x in wis])
+        axs = (C.c_void_p * count)(*[x.ctypes.data for x in was])
+        ra, sa = fr_np([x for x, _ in rs]), fr_np([y for _, y in rs])
+        out = np.zeros((count, 256), dtype=np.uint8)
+        for rep in range(2):      # the second call reuses the batch workspaces
+            out[:] = 0
+            fb.native.check(fb.native.lib.fb_prove_batch(ctx.handle, pk, count, ins, 2, axs, len(aux), ra.ctypes.data,
+                                                         sa.ctypes.data, out.ctypes.data))
+            for i, (r, s) in enumerate(rs):
+                ref = og.prove(P, gates, wits[i][0], wits[i][1], r, s)
+                assert out[i].tobytes() == codec.proof_raw(ref), (rep, i)
+        # a wrong-shaped witness is refused
+        rc = fb.native.lib.fb_prove_batch(ctx.handle, pk, count, ins, 2, axs, len(aux) - 1, ra.ctypes.data, sa.ctypes.data,
+                                          out.ctypes.data)
+        assert rc == -1
+        params.unload()
+    finally:
+        fb.native.lib.fb_set_msm_tables(-1)
+        os.environ.pop("FB_BATCH_MODE", None)
+        os.environ.pop("FB_BATCH_P", None)
 
 
 def test_prove_stream_matches_single_proofs(ctx):
