@@ -336,8 +336,6 @@ static int load_key_once(Ctx* ctx, const uint8_t* params, size_t len, const Circ
   const MsmPlan msm_plans[4] = {pk->plan_h, pk->plan_l, pk->plan_a, pk->plan_b};
   int arc = 0;
   for (int i = 0; i < 4 && !arc; i++) arc = pk->msm[i].alloc(&msm_plans[i], 1, i == 3);
-  if (!arc && g_msm_batch_affine)  // optional buffers: a scratch that cannot get them accumulates in XYZZ only
-    for (int i = g_msm_batch_affine == 3 ? 3 : 0; i < 4; i++) pk->msm[i].alloc_batch_affine(&msm_plans[i], 1, i == 3);
   if (arc != 0) {
     set_error("MSM scratch allocation failed");
     pk_release(pk);
@@ -492,7 +490,6 @@ static void* build_host_tables(const ProvingKey* pk) {
 }
 
 int g_msm_tables = -1;
-int g_msm_batch_affine = 0;
 static bool g_serial = false;  // one stream, MSMs back to back (used for per-kernel timing)
 static std::atomic<int> g_prove_graph{-1}; // CUDA-graph replay for small keys: -1 = on unless FB_PROVE_GRAPH=0, 0 off, 1 on
 bool kstat_enabled();
@@ -1014,7 +1011,7 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
   info->msm_window_bits = pk->plan_h.c;
   info->msm_windows = pk->plan_h.W;
   info->msm_tables = pk->plan_h.table ? 1 : 0;
-  info->msm_batch_affine = (pk->msm[0].ba_cap || pk->msm[3].ba_cap) ? 1 : 0;
+  info->reserved0 = 0;
   info->table_bytes = pk->table_bytes;
   return FB_OK;
 }
@@ -1618,7 +1615,6 @@ uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
 void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 : 0); }
 void fb_set_prove_graph(int on) { fb::g_prove_graph.store(on ? 1 : 0); }
-void fb_set_msm_batch_affine(int on) { fb::g_msm_batch_affine = (on < 0 || on > 3) ? 0 : on; }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
 int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {

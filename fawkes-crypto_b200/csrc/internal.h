@@ -20,9 +20,6 @@ namespace fb {
 void set_error(const char* fmt, ...);
 // MSM window tables (msm.cuh): -1 auto (on when the tables fit in free HBM with headroom), 0 off, 1 on
 extern int g_msm_tables;
-// batch-affine pre-reduction in front of the XYZZ bucket accumulation (msm.cu): 0 off (default: measured
-// slower than the XYZZ kernel), 1 on, 2 on even for small inputs (tests)
-extern int g_msm_batch_affine;
 
 // ---- instrumentation (bench.py: gpu_launches and the live roofline timing) -------------
 extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library

@@ -13,21 +13,22 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   MsmPlan p;
   p.n = n;
   p.table = table;
-  p.ba_force = g_msm_batch_affine == 2;
   int lg = 0;
   while ((2u << lg) <= n && lg < 31) lg++;
   int c;
   if (table) {
     // One bucket set for all windows: n*W mixed adds to accumulate, and sort + reduction work per bucket
     // worth ~20 mixed adds (measured: 2^24 rows c = 20 beats 22 by 9 ms, 2^20 rows c = 17 beats 19 by
-    // 1.5 ms; profiles/r01_window_sweep.txt).  Windows whose top digit has only a few bits are skipped:
-    // all n top digits would land in a handful of buckets (c = 21 / 23 at 2^24 cost +30 / +70 ms).
+    // 1.5 ms; profiles/r01_window_sweep.txt).  Windows whose top digit has only a few bits are skipped WHEN n is
+    // large: all n top digits then land in a handful of buckets, tens of thousands of atomics per counter in the
+    // digit sort (c = 21 / 23 at 2^24 cost +30 / +70 ms).  Small circuits keep them: at n = 8191 the rule left only
+    // c = 8 (32 digits per scalar, every bucket "heavy") where c = 10 needs 26 (profiles/r02_cfg2_batch_launches.csv).
     double best = 1e300;
     c = 0;
     for (int cand = std::max(4, lg - 6); cand <= std::min(22, std::max(4, lg)); cand++) {
       const int Wc = (255 + cand - 1) / cand;
       const int top_bits = 254 - (Wc - 1) * cand;
-      if (2 * top_bits < cand) continue;
+      if (2 * top_bits < cand && (n >> std::max(top_bits, 0)) > 65536u) continue;
       const double cost = (double)n * Wc + 20.0 * (double)(1u << (cand - 1));
       if (cost < best) { best = cost; c = cand; }
     }
@@ -51,6 +52,7 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   int tl = 4;
   while (tl < 8 && (1ull << tl) < want) tl++;
   if (tl < MSM_MIN_TASK_LOG) tl = MSM_MIN_TASK_LOG;
+  tl = std::max(tl, p.task_log_for_bucket_size());
   if (const char* e = getenv("FB_MSM_TASK_LOG")) {
     int v = atoi(e);
     if (v >= MSM_MIN_TASK_LOG && v <= 10) tl = v;
@@ -67,8 +69,17 @@ MsmPlan MsmPlan::batched(uint32_t nsets, uint64_t stride) const {
   uint64_t want = p.entries() >> 18;
   int tl = 4;
   while (tl < 8 && (1ull << tl) < want) tl++;
-  p.task_log = tl;
+  p.task_log = std::max(tl, p.task_log_for_bucket_size());
   return p;
+}
+
+// Tasks long enough that an average bucket is covered by at most ~24 of them (MSM_HEAVY = 32 partial sums is where a
+// bucket goes onto the "heavy" path): with few, big buckets short tasks would make every bucket heavy.
+int MsmPlan::task_log_for_bucket_size() const {
+  const uint64_t per_bucket = (uint64_t)n * W / std::max<uint32_t>(table ? B : B * (uint32_t)W, 1u);
+  int tl = MSM_MIN_TASK_LOG;
+  while (tl < 8 && (24ull << tl) < per_bucket) tl++;
+  return tl;
 }
 
 // segments one k_segment_bits CTA folds (per (window, bit) job the segment range is cut into parts)
@@ -87,9 +98,6 @@ int MsmScratch::alloc(const MsmPlan* plans, int count, bool need_g2) {
     ent = std::max<uint64_t>(ent, p.entries());
     bk = std::max<uint64_t>(bk, p.nbuckets());
     tk = std::max<uint64_t>(tk, (p.entries() >> p.task_log) + p.nbuckets() + 2);
-    // the XYZZ pass after the batch-affine rounds runs short tasks over the reduced list
-    tk = std::max<uint64_t>(tk, ((((p.entries()) >> p.ba_rounds()) + p.nbuckets() + 1) >> MSM_MIN_TASK_LOG) +
-                                    p.nbuckets() + 2);
     vp = std::max<uint64_t>(vp, (uint64_t)p.wred() * (p.c - p.seg_log) * bits_parts(p));
   }
   cap_entries = ent;
@@ -113,41 +121,10 @@ int MsmScratch::alloc(const MsmPlan* plans, int count, bool need_g2) {
   return 0;
 }
 
-// Buffers of the batch-affine rounds, sized for the largest plan.  Failure (out of memory) is not an
-// error: the scratch simply runs without the pre-reduction.
-int MsmScratch::alloc_batch_affine(const MsmPlan* plans, int count, bool need_g2) {
-  uint64_t ent = 0, bk = 1;
-  for (int i = 0; i < count; i++) {
-    if (plans[i].n == 0 || plans[i].ba_rounds() == 0) continue;
-    ent = std::max<uint64_t>(ent, plans[i].entries());
-    bk = std::max<uint64_t>(bk, plans[i].nbuckets());
-  }
-  if (ent == 0) return 0;
-  const size_t fsz = need_g2 ? sizeof(Fq2) : sizeof(Fq);
-  const uint64_t l1 = ent / 2 + bk + 1, l2 = ent / 4 + bk + 1;  // outputs of the first / second level
-  bool ok = cudaMalloc(&ba_off, (size_t)MSM_BA_MAX_ROUNDS * (bk + 1) * 4) == cudaSuccess &&
-            cudaMalloc(&ba_cnt, (bk + 1) * 4) == cudaSuccess &&
-            cudaMalloc(&ba_src, (ent + (uint64_t)MSM_BA_MAX_ROUNDS * (bk + 1)) * 4) == cudaSuccess &&
-            cudaMalloc(&ba_pr, l1 * fsz) == cudaSuccess &&
-            cudaMalloc(&ba_pts[0], l1 * 2 * fsz) == cudaSuccess &&
-            cudaMalloc(&ba_pts[1], l2 * 2 * fsz) == cudaSuccess;
-  if (!ok) {
-    cudaGetLastError();
-    cudaFree(ba_off); cudaFree(ba_cnt); cudaFree(ba_src); cudaFree(ba_pr); cudaFree(ba_pts[0]); cudaFree(ba_pts[1]);
-    ba_off = ba_cnt = ba_src = nullptr; ba_pr = ba_pts[0] = ba_pts[1] = nullptr;
-    ba_cap = 0;
-    return 1;
-  }
-  ba_cap = ent;
-  return 0;
-}
-
 void MsmScratch::release() {
   cudaFree(hist); cudaFree(offsets); cudaFree(cursor); cudaFree(blocksums); cudaFree(sorted);
   cudaFree(buckets); cudaFree(segR); cudaFree(segS); cudaFree(winsum);
   cudaFree(ntasks); cudaFree(task_off); cudaFree(partials); cudaFree(heavy);
-  cudaFree(ba_off); cudaFree(ba_cnt); cudaFree(ba_src); cudaFree(ba_pr); cudaFree(ba_pts[0]); cudaFree(ba_pts[1]);
-  ba_off = ba_cnt = ba_src = nullptr; ba_pr = ba_pts[0] = ba_pts[1] = nullptr; ba_cap = 0;
   ntasks = task_off = heavy = nullptr; partials = nullptr;
   hist = offsets = cursor = blocksums = sorted = nullptr;
   buckets = segR = segS = winsum = nullptr;
@@ -275,7 +252,6 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t* __restrict__ cu
 // the points is simply spread over thousands of threads).  The partial of (bucket b, thread t)
 // lives at index b + t: bucket b owns the contiguous slots b + floor(start_b / T) .. b +
 // floor((end_b - 1) / T), so no second scan is needed to find them.
-// DIRECT: `bases` already holds the points in sorted order (output of the batch-affine rounds).
 #ifndef MSM_LD64_DEFAULT
 #define MSM_LD64_DEFAULT 1
 #endif
@@ -303,7 +279,7 @@ __device__ __forceinline__ Affine<F> load_base(const Affine<F>* __restrict__ p, 
   return *p;
 }
 
-template <class F, bool DIRECT>
+template <class F>
 __global__ void __launch_bounds__(128, MSM_ACC_MIN_CTAS(F))
 k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
              const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
@@ -326,9 +302,9 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
   // in registers spills (255 registers either way), so the next point is only prefetched into L2 and
   // loaded at the top of its own iteration -- an L2 hit against a 17k-cycle add.
   constexpr bool REG_PREFETCH = sizeof(F) == sizeof(Fq);
-  uint32_t e = DIRECT ? 0u : sorted[start];
+  uint32_t e = sorted[start];
   Affine<F> nxt;
-  if (REG_PREFETCH) nxt = DIRECT ? bases[start] : load_base(bases + (e & 0x7fffffffu), ld64);
+  if (REG_PREFETCH) nxt = load_base(bases + (e & 0x7fffffffu), ld64);
   for (uint32_t p = start; p < end; p++) {
     if (p >= bend) {  // bucket boundary: flush and move on (empty buckets are skipped)
       partials[b + t] = acc;
@@ -340,18 +316,14 @@ k_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ s
     if (REG_PREFETCH) {
       cur = nxt;
       if (p + 1 < end) {
-        if (DIRECT) {
-          nxt = bases[p + 1];
-        } else {
-          e = sorted[p + 1];
-          nxt = load_base(bases + (e & 0x7fffffffu), ld64);
-        }
+        e = sorted[p + 1];
+        nxt = load_base(bases + (e & 0x7fffffffu), ld64);
       }
     } else {
-      const Affine<F>* src = DIRECT ? bases + p : bases + (e & 0x7fffffffu);
+      const Affine<F>* src = bases + (e & 0x7fffffffu);
       if (p + 1 < end) {
-        if (!DIRECT) e = sorted[p + 1];
-        const Affine<F>* nsrc = DIRECT ? bases + p + 1 : bases + (e & 0x7fffffffu);
+        e = sorted[p + 1];
+        const Affine<F>* nsrc = bases + (e & 0x7fffffffu);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc));
       }
       cur = *src;
@@ -543,213 +515,6 @@ k_build_window_table(Affine<F>* __restrict__ tab, uint32_t n, int c, int W) {
   }
 }
 
-// ------------------------------------------------------ batch-affine rounds ---
-// OPTIONAL (fb_set_msm_batch_affine, off by default): exact and tested, but on B200 the rounds run at
-// 6.2e9 G1 adds/s (2.1 TB/s of mostly 32-64 B accesses) against 7.4e9 for the XYZZ kernel -- the
-// ~340 B of HBM traffic per add (two passes over the operands plus the prefix products) eats what the
-// cheaper formula saves.  Kept as the starting point for a shared-memory-staged version.
-// The accumulation kernels sit on the wide-MAC issue limit, so the way to go faster is fewer MACs per
-// bucket add.  An affine add is 1 sqr + 2 mul once 1/(x2 - x1) is known, and Montgomery's trick turns
-// K inversions into one plus 3 mul each: 5 mul + 1 sqr (~3200 cycles) against 5450 for the XYZZ mixed
-// add.  Each round adds the entries of every bucket pairwise (an odd one is carried over), halving the
-// list; after `ba_rounds()` rounds ~12-24 points per bucket are left for the XYZZ kernel above.
-//   k_ba_counts + scan   offsets of the next level: ceil(count / 2) per bucket
-//   k_ba_src             per output slot: first input slot, and whether it is a pair
-//   k_ba_round           thread t owns K consecutive output slots: forward pass stores the prefix
-//                        products of its pairs' x differences, one inversion, backward pass emits the sums
-// Pairs that cannot use the chord formula (equal x: doubling or inverse points; a point at infinity)
-// are left out of the product and take an exact slow path with their own inversion.
-constexpr uint32_t BA_PAIR = 0x80000000u;
-
-__global__ void k_ba_counts(const uint32_t* __restrict__ off_prev, uint32_t nb, uint32_t* __restrict__ cnt) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < nb) cnt[b] = (off_prev[b + 1] - off_prev[b] + 1) >> 1;
-  if (b == nb) cnt[b] = 0;
-}
-
-__global__ void k_ba_src(const uint32_t* __restrict__ off_prev, const uint32_t* __restrict__ off_cur, uint32_t nb,
-                         uint32_t* __restrict__ src) {
-  const uint32_t total = off_cur[nb];
-  const uint32_t start = (blockIdx.x * blockDim.x + threadIdx.x) << 5;
-  if (start >= total) return;
-  const uint32_t end = min(start + 32u, total);
-  uint32_t lo = 0, hi = nb;
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (off_cur[mid] <= start) lo = mid; else hi = mid;
-  }
-  uint32_t b = lo, bend = off_cur[b + 1];
-  for (uint32_t o = start; o < end; o++) {
-    while (o >= bend) { b++; bend = off_cur[b + 1]; }
-    const uint32_t j = o - off_cur[b];
-    const uint32_t p0 = off_prev[b], cntp = off_prev[b + 1] - p0;
-    src[o] = (p0 + 2 * j) | ((2 * j + 1 < cntp) ? BA_PAIR : 0u);
-  }
-}
-
-template <class F, bool LEVEL0>
-__device__ __forceinline__ Affine<F> ba_fetch(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
-                                              uint32_t i) {
-  if (LEVEL0) {
-    const uint32_t e = sorted[i];
-    Affine<F> p = pts[e & 0x7fffffffu];
-    if (e >> 31) p.y = neg(p.y);
-    return p;
-  }
-  return pts[i];
-}
-template <class F, bool LEVEL0>
-__device__ __forceinline__ F ba_fetch_x(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted, uint32_t i) {
-  if (LEVEL0) return pts[sorted[i] & 0x7fffffffu].x;
-  return pts[i].x;
-}
-// exact P + Q for the pairs the chord formula cannot take
-template <class F>
-__device__ __noinline__ Affine<F> ba_add_slow(const Affine<F>& P, const Affine<F>& Q) {
-  if (P.is_inf()) return Q;
-  if (Q.is_inf()) return P;
-  if (P.x != Q.x) {  // not reached from k_ba_round; kept so the function is a complete addition
-    const F lam = mul(sub(Q.y, P.y), inv_cold(sub(Q.x, P.x)));
-    const F x3 = sub(sub(sqr(lam), P.x), Q.x);
-    return {x3, sub(mul(lam, sub(P.x, x3)), P.y)};
-  }
-  if (P.y != Q.y || P.y.is_zero()) return Affine<F>::inf();
-  const F x2 = sqr(P.x);
-  const F lam = mul(add(dbl(x2), x2), inv_cold(dbl(P.y)));
-  const F x3 = sub(sqr(lam), dbl(P.x));
-  return {x3, sub(mul(lam, sub(P.x, x3)), P.y)};
-}
-
-// warp shuffles of field elements
-__device__ __forceinline__ Fq shfl_up_f(const Fq& v, int d) {
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = __shfl_up_sync(0xffffffffu, v.v[i], d);
-  return r;
-}
-__device__ __forceinline__ Fq shfl_down_f(const Fq& v, int d) {
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
-  return r;
-}
-__device__ __forceinline__ Fq shfl_f(const Fq& v, int lane) {
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], lane);
-  return r;
-}
-__device__ __forceinline__ Fq2 shfl_up_f(const Fq2& v, int d) { return {shfl_up_f(v.c0, d), shfl_up_f(v.c1, d)}; }
-__device__ __forceinline__ Fq2 shfl_down_f(const Fq2& v, int d) { return {shfl_down_f(v.c0, d), shfl_down_f(v.c1, d)}; }
-__device__ __forceinline__ Fq2 shfl_f(const Fq2& v, int lane) { return {shfl_f(v.c0, lane), shfl_f(v.c1, lane)}; }
-
-// 1 / acc for every lane of the warp with ONE field inversion: prefix and suffix products across the
-// lanes (two 5-step scans), invert the warp total, multiply back.  All 32 lanes must call it.
-template <class F>
-__device__ __noinline__ F warp_batch_inverse(F acc) {
-  const int lane = threadIdx.x & 31;
-  F x = acc, y = acc;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const F t = shfl_up_f(x, d);
-    const F u = shfl_down_f(y, d);
-    const F mx = mul(x, t), my = mul(y, u);
-    if (lane >= d) x = mx;
-    if (lane + d < 32) y = my;
-  }
-  const F tot = shfl_f(x, 31);
-  F E = shfl_up_f(x, 1), S = shfl_down_f(y, 1);
-  if (lane == 0) E = F::one();
-  if (lane == 31) S = F::one();
-  return mul(inv_cold(tot), mul(E, S));
-}
-
-template <class F>
-struct BaPair {
-  Affine<F> P, Q;
-  uint32_t s;
-};
-template <class F, bool LEVEL0>
-__device__ __forceinline__ void ba_load(BaPair<F>& c, const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted,
-                                        const uint32_t* __restrict__ src, uint32_t o) {
-  c.s = src[o];
-  const uint32_t i0 = c.s & ~BA_PAIR;
-  c.P = ba_fetch<F, LEVEL0>(pts, sorted, i0);
-  if (c.s & BA_PAIR) c.Q = ba_fetch<F, LEVEL0>(pts, sorted, i0 + 1);
-}
-
-template <class F, bool LEVEL0>
-__global__ void __launch_bounds__(128)
-k_ba_round(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ src,
-           const uint32_t* __restrict__ off_cur, uint32_t nb, int klog, F* __restrict__ pr, Affine<F>* __restrict__ out) {
-  const uint32_t total = off_cur[nb];
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (((tid & ~31u) << klog) >= total) return;  // whole warp past the end (warp-uniform)
-  uint32_t start = min(tid << klog, total);
-  const uint32_t end = min(start + (1u << klog), total);
-  // forward: prefix products of the x differences of this thread's regular pairs, two slots per step so
-  // that four gathers are in flight per thread
-  F acc = F::one();
-  for (uint32_t o = start; o < end; o += 2) {
-    const uint32_t s0 = src[o], s1 = o + 1 < end ? src[o + 1] : 0u;
-    F xa = F::zero(), xb = F::zero(), xc = F::zero(), xd = F::zero();
-    if (s0 & BA_PAIR) {
-      xa = ba_fetch_x<F, LEVEL0>(pts, sorted, s0 & ~BA_PAIR);
-      xb = ba_fetch_x<F, LEVEL0>(pts, sorted, (s0 & ~BA_PAIR) + 1);
-    }
-    if (s1 & BA_PAIR) {
-      xc = ba_fetch_x<F, LEVEL0>(pts, sorted, s1 & ~BA_PAIR);
-      xd = ba_fetch_x<F, LEVEL0>(pts, sorted, (s1 & ~BA_PAIR) + 1);
-    }
-    // equal x, or x = 0 (infinity, or one of the few curve points with x = 0): not part of the product; the
-    // backward pass applies the same predicate and adds those pairs exactly
-    if (s0 & BA_PAIR) {
-      const F dx = sub(xb, xa);
-      if (!dx.is_zero() && !xa.is_zero() && !xb.is_zero()) acc = mul(acc, dx);
-    }
-    pr[o] = acc;
-    if (o + 1 < end) {
-      if (s1 & BA_PAIR) {
-        const F dx = sub(xd, xc);
-        if (!dx.is_zero() && !xc.is_zero() && !xd.is_zero()) acc = mul(acc, dx);
-      }
-      pr[o + 1] = acc;
-    }
-  }
-  F iv = warp_batch_inverse(acc);
-  // backward: peel the inverses off and emit the sums; the next slot's points are fetched while the
-  // current pair is being added
-  if (start >= end) return;
-  // (G1 only: a second G2 pair in registers spills)
-  constexpr bool PREFETCH = sizeof(F) == sizeof(Fq);
-  BaPair<F> cur, nxt;
-  if (PREFETCH) ba_load<F, LEVEL0>(cur, pts, sorted, src, end - 1);
-  for (uint32_t o = end; o-- > start;) {
-    F prev = F::one();
-    if (PREFETCH) {
-      if (o > start) ba_load<F, LEVEL0>(nxt, pts, sorted, src, o - 1);
-    } else {
-      ba_load<F, LEVEL0>(cur, pts, sorted, src, o);
-    }
-    if (o > start) prev = pr[o - 1];
-    if (!(cur.s & BA_PAIR)) {
-      out[o] = cur.P;
-    } else {
-      const F dx = sub(cur.Q.x, cur.P.x);
-      if (dx.is_zero() || cur.P.x.is_zero() || cur.Q.x.is_zero()) {
-        out[o] = ba_add_slow(cur.P, cur.Q);
-      } else {
-        const F idx = mul(iv, prev);
-        iv = mul(iv, dx);
-        const F lam = mul(sub(cur.Q.y, cur.P.y), idx);
-        const F x3 = sub(sub(sqr(lam), cur.P.x), cur.Q.x);
-        out[o] = {x3, sub(mul(lam, sub(cur.P.x, x3)), cur.P.y)};
-      }
-    }
-    if (PREFETCH) cur = nxt;
-  }
-}
-
 // ----------------------------------------------------------------- driver ---
 template <class F>
 static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* map,
@@ -786,64 +551,14 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   XYZZ<F>* partials = reinterpret_cast<XYZZ<F>*>(s.partials);
   const uint64_t N = p.entries();
   const int kind = sizeof(F) == sizeof(Fq) ? KSTAT_ACC_G1 : KSTAT_ACC_G2;
-  // ---- batch-affine rounds: sorted entries -> ~N / 2^R affine points, still grouped by bucket
-  // mode 3: G2 only (an Fq2 add is 2.5x the MACs of an Fq one for 2x the bytes, so the rounds pay there first)
-  const bool ba_on = g_msm_batch_affine == 1 || g_msm_batch_affine == 2 ||
-                     (g_msm_batch_affine == 3 && sizeof(F) == sizeof(Fq2));
-  int R = (ba_on && s.ba_cap >= N) ? p.ba_rounds() : 0;
-  if (const char* e = getenv("FB_MSM_BA_ROUNDS")) R = std::min(R, atoi(e));
   const uint32_t* offsets = s.offsets;
-  const Affine<F>* acc_pts = bases;
-  int task_log = p.task_log;
-  uint64_t acc_entries = N;
+  const int task_log = p.task_log;
   kstat_begin(kind, st);
-  if (R > 0) {
-    const unsigned nbb = (nb + 1 + 255) / 256, sb = (nb + 1 + 1023) / 1024;
-    const uint32_t* off_prev = s.offsets;
-    const Affine<F>* in_pts = bases;
-    uint32_t* src = s.ba_src;
-    for (int r = 1; r <= R; r++) {
-      uint32_t* off_cur = s.ba_off + (size_t)(r - 1) * (nb + 1);
-      const uint64_t bound = (N >> r) + nb + 1;  // upper bound of this level's length
-      if (!reuse_sort) {  // the level structure depends on the sort only: B_g1 reuses B_g2's
-        k_ba_counts<<<nbb, 256, 0, st>>>(off_prev, nb, s.ba_cnt);
-        k_scan_block<<<sb, 1024, 0, st>>>(s.ba_cnt, off_cur, s.blocksums, nb + 1);
-        k_scan_sums<<<1, 1024, 0, st>>>(s.blocksums, sb);
-        k_scan_add<<<sb, 1024, 0, st>>>(off_cur, nullptr, s.blocksums, nb + 1);
-        k_ba_src<<<(unsigned)((bound + 32 * 128 - 1) / (32 * 128)), 128, 0, st>>>(off_prev, off_cur, nb, src);
-        count_launch(5);
-      }
-      // outputs per thread (one inversion per WARP): enough threads to fill the chip, at most 256
-      int klog = 8;
-      while (klog > 4 && (bound >> klog) < 148ull * 640) klog--;
-      Affine<F>* out_pts = reinterpret_cast<Affine<F>*>(s.ba_pts[(r - 1) & 1]);
-      const unsigned grid = (unsigned)(((bound >> klog) + 1 + 127) / 128);
-      if (r == 1)
-        k_ba_round<F, true><<<grid, 128, 0, st>>>(in_pts, s.sorted, src, off_cur, nb, klog,
-                                                 reinterpret_cast<F*>(s.ba_pr), out_pts);
-      else
-        k_ba_round<F, false><<<grid, 128, 0, st>>>(in_pts, nullptr, src, off_cur, nb, klog,
-                                                  reinterpret_cast<F*>(s.ba_pr), out_pts);
-      count_launch(1);
-      src += bound;
-      off_prev = off_cur;
-      in_pts = out_pts;
-    }
-    offsets = off_prev;
-    acc_pts = in_pts;
-    acc_entries = (N >> R) + nb + 1;
-    task_log = MSM_MIN_TASK_LOG;
-    while (task_log < 8 && (acc_entries >> task_log) > (1u << 19)) task_log++;
-  }
-  const uint64_t max_threads = (acc_entries >> task_log) + 1;
+  const uint64_t max_threads = (N >> task_log) + 1;
   if (max_threads + nb > s.cap_tasks) return -4;
   cudaMemsetAsync(s.heavy, 0, 4, st);
-  if (R > 0)
-    k_accumulate<F, true><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(acc_pts, nullptr, offsets, nb,
-                                                                                task_log, partials, 0);
-  else
-    k_accumulate<F, false><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb,
-                                                                                 p.task_log, partials, msm_ld64());
+  k_accumulate<F><<<(unsigned)((max_threads + 127) / 128), 128, 0, st>>>(bases, s.sorted, s.offsets, nb, p.task_log, partials,
+                                                                      msm_ld64());
   kstat_end(kind, st);
   count_launch(reuse_sort ? 5 : 10);
   kstat_begin(KSTAT_REDUCE, st);

@@ -15,7 +15,6 @@
 //   3. k_digits<1>     counting-sort placement of (w * n + i | sign << 31)
 //   4. k_accumulate    equal-length tasks of 2^task_log sorted entries per thread, XYZZ mixed adds, a partial
 //                      flushed at every bucket change; k_bucket_gather / k_bucket_heavy fold the partials
-//      (optional: k_ba_* batch-affine rounds in front of it, off by default -- see msm.cu)
 //   5. k_bucket_segments / k_segment_bits / k_fold_parts   per-segment short running sums, then the segment
 //                      sums combined bit-wise into V[p] (weight 2^p)
 //   6. (host)          sum_p 2^p V[p] by Horner on a CPU core: msm_horner_host
@@ -32,7 +31,6 @@ constexpr int MSM_MIN_TASK_LOG = 4;
 constexpr uint32_t MSM_MIN_TASK = 1u << MSM_MIN_TASK_LOG;
 constexpr uint32_t MSM_HEAVY = 32;        // partials per bucket handled by one thread
 constexpr int MSM_HEAVY_THREADS = 128;
-constexpr int MSM_BA_MAX_ROUNDS = 6;
 constexpr int MSM_VBITS = 288;            // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
 
 struct MsmPlan {
@@ -55,6 +53,7 @@ struct MsmPlan {
   bool batched_out = false;  // result array holds vbits() entries (set p at p * vbits_per_set()), not MSM_VBITS
   static MsmPlan make(uint32_t n, bool table = false);
   MsmPlan batched(uint32_t nsets, uint64_t stride) const;      // same window, task size for the whole batch
+  int task_log_for_bucket_size() const;
   uint64_t entries() const { return (uint64_t)n * W * sets; }  // digits to sort and accumulate (upper bound)
   int wred() const { return (int)sets * (table ? 1 : W); }     // bucket sets to reduce
   int vbits_per_set() const { return (table ? 1 : W) * c; }    // V entries of one scalar vector
@@ -62,15 +61,6 @@ struct MsmPlan {
   uint32_t nsegs() const { return nbuckets() >> seg_log; }
   int vbits() const { return wred() * c; }                     // V entries the host Horner consumes
   uint64_t table_points() const { return table ? (uint64_t)n * W : n; }
-  // batch-affine rounds before the XYZZ accumulation: halve the entries per bucket until ~12 are left
-  bool ba_force = false;  // tests: run the rounds on small inputs too (fb_set_msm_batch_affine(2))
-  int ba_rounds() const {
-    const uint64_t N = (uint64_t)n * W;
-    if (!ba_force && N < (1u << 16)) return 0;
-    int r = 0;
-    while (r < MSM_BA_MAX_ROUNDS && (N >> (r + 1)) >= (ba_force ? 1ull : 12ull) * nbuckets()) r++;
-    return r;
-  }
 };
 
 // Scratch shared by consecutive MSMs on one stream (sized for the largest plan).
@@ -88,16 +78,8 @@ struct MsmScratch {
   uint32_t* task_off = nullptr; // [nbuckets + 1]
   void* partials = nullptr;     // [cap_tasks] XYZZ
   uint32_t* heavy = nullptr;    // [0] = count, then bucket ids
-  // batch-affine pre-reduction (msm.cu, "batch-affine rounds"); all null when the scratch was allocated without
-  uint32_t* ba_off = nullptr;   // [MSM_BA_MAX_ROUNDS][nbuckets + 1] bucket offsets of every level
-  uint32_t* ba_cnt = nullptr;   // [nbuckets + 1]
-  uint32_t* ba_src = nullptr;   // per level: first input slot of every output slot (| pair flag)
-  void* ba_pr = nullptr;        // prefix products of the round in flight (one field element per output slot)
-  void* ba_pts[2] = {nullptr, nullptr};  // affine points of the odd / even levels
-  uint64_t ba_cap = 0;          // entries the batch-affine buffers were sized for (0 = disabled)
   size_t cap_entries = 0, cap_buckets = 0, cap_tasks = 0;
   int alloc(const MsmPlan* plans, int count, bool need_g2);
-  int alloc_batch_affine(const MsmPlan* plans, int count, bool need_g2);  // optional, after alloc()
   void release();
 };
 

@@ -8,7 +8,6 @@
 #include <vector>
 
 #include "internal.h"
-#include "ff29.cuh"
 
 namespace fb {
 
@@ -172,19 +171,6 @@ __global__ void k_probe_fr_mul_v(Fr* out, int iters) {
   if (x.v[0] == 0x12345678u && y.v[3] == 0x9abcdef0u) out[0] = x;
 #endif
 }
-// lazy 29-bit multiplier: VARIANT 0 mul/mul, 1 sqr + add + sub (the non-multiply mix of a point add)
-template <int VARIANT>
-__global__ void k_probe_fr29(Fr* out, int iters) {
-  Fr29 x = Fr29::one(), y = Fr29::one();
-  x.l[0] += threadIdx.x;
-  y.l[1] ^= blockIdx.x & 0xff;
-  for (int i = 0; i < iters; i++) {
-    if (VARIANT == 0) { x = mul(x, y); y = mul(y, x); }
-    else { x = sqr(x); y = add(y, x); x = sub(x, y); }
-  }
-  if (x.l[0] == 0x12345678u && y.l[3] == 0x9abcdefu) out[0].v[0] = x.l[2];
-}
-
 __global__ void k_probe_fr_mul(Fr* out, int iters) {
   Fr x = Fr::one(), y = Fr::r2();
   x.v[0] += threadIdx.x;
@@ -321,7 +307,6 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   }
   MsmScratch scr;
   if (scr.alloc(&plan, 1, group == 2) != 0) { set_error("msm scratch alloc failed"); return FB_ERR_CUDA; }
-  if (g_msm_batch_affine) scr.alloc_batch_affine(&plan, 1, group == 2);
   std::vector<G2XYZZ> hres(MSM_VBITS);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -415,8 +400,6 @@ int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, doubl
     else if (which == 6) k_probe_mac_shape<1><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
     else if (which == 7) k_probe_mac_shape<2><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
     else if (which == 8) k_probe_mac_shape<3><<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, 777u + rep, iters);
-    else if (which == 3) k_probe_fr29<0><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
-    else if (which == 4) k_probe_fr29<1><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
     else k_probe_fr_mul_v<1><<<blocks, threads, 0, ctx->stream>>>((Fr*)d, iters);
     cudaEventRecord(e1, ctx->stream);
     FB_CUDA(cudaStreamSynchronize(ctx->stream));

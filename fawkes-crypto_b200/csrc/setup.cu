@@ -14,6 +14,7 @@
 #include "../../include/fawkes_b200.h"
 
 #include <cstring>
+#include <thread>
 
 #include "host_fr.h"
 #include "internal.h"
@@ -157,6 +158,30 @@ struct FixedBase {
   }
 };
 
+// host loops of the setup (powers of tau, query scalars) split over the host cores
+template <class Fn>
+static void host_parallel(uint64_t n, Fn fn) {
+  const unsigned T = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min(32u, std::max(1u, std::thread::hardware_concurrency())), n / 65536));
+  if (T <= 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const uint64_t chunk = (n + T - 1) / T;
+  for (unsigned t = 0; t < T; t++) {
+    const uint64_t lo = t * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([=] { fn(lo, hi); });
+  }
+  for (auto& x : th) x.join();
+}
+static hfr::H host_pow(hfr::H a, uint64_t e) {
+  hfr::H r = hfr::one();
+  while (e) {
+    if (e & 1) r = hfr::mul(r, a);
+    a = hfr::mul(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+
 static inline hfr::H H_of(const uint64_t x[4]) { hfr::H h; memcpy(h.v, x, 32); return h; }
 static inline hfr::H H_of(const Fr& x) { hfr::H h; memcpy(h.v, x.v, 32); return h; }
 static inline Fr F_of(const hfr::H& h) { Fr r; memcpy(r.v, h.v, 32); return r; }
@@ -209,53 +234,68 @@ static int setup_impl(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t tr
   if (hfr::is_zero(gamma) || hfr::is_zero(delta)) { set_error("gamma/delta must be non-zero"); return FB_ERR_ARG; }
   // powers of tau, h scalars
   std::vector<hfr::H> pw(m);
-  pw[0] = hfr::one();
-  for (uint64_t i = 1; i < m; i++) pw[i] = hfr::mul(pw[i - 1], tau);
+  host_parallel(m, [&](uint64_t lo, uint64_t hi) {
+    hfr::H u = host_pow(tau, lo);
+    for (uint64_t i = lo; i < hi; i++) { pw[i] = u; u = hfr::mul(u, tau); }
+  });
   const hfr::H z_tau = hfr::sub(hfr::mul(pw[m - 1], tau), hfr::one());
   const hfr::H dinv = hfr::inv(delta), ginv = hfr::inv(gamma);
   const hfr::H hcoef = hfr::mul(z_tau, dinv);
   std::vector<Fr> h_s(m - 1);
-  for (uint64_t i = 0; i + 1 < m; i++) h_s[i] = F_of(hfr::mul(pw[i], hcoef));
+  host_parallel(m - 1, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) h_s[i] = F_of(hfr::mul(pw[i], hcoef));
+  });
   // Lagrange values at tau: ifft of the powers (on the GPU)
   {
     NttDomain dom;
     if (dom.init(k, st) != 0) { set_error("domain init failed"); return FB_ERR_CUDA; }
-    Fr *dx, *ds;
-    FB_CUDA(cudaMalloc(&dx, m * sizeof(Fr)));
-    FB_CUDA(cudaMalloc(&ds, m * sizeof(Fr)));
-    FB_CUDA(cudaMemcpyAsync(dx, pw.data(), m * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    dom.transform(dx, ds, 1, st);
-    FB_CUDA(cudaMemcpyAsync(pw.data(), dx, m * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+    struct Dev {  // freed on every exit path
+      Fr* p = nullptr;
+      ~Dev() { if (p) cudaFree(p); }
+    } dx, ds;
+    struct DomGuard {
+      NttDomain& d;
+      ~DomGuard() { d.destroy(); }
+    } dom_guard{dom};
+    FB_CUDA(cudaMalloc(&dx.p, m * sizeof(Fr)));
+    FB_CUDA(cudaMalloc(&ds.p, m * sizeof(Fr)));
+    FB_CUDA(cudaMemcpyAsync(dx.p, pw.data(), m * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    dom.transform(dx.p, ds.p, 1, st);
+    FB_CUDA(cudaMemcpyAsync(pw.data(), dx.p, m * sizeof(Fr), cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(dx);
-    cudaFree(ds);
-    dom.destroy();
   }
   const std::vector<hfr::H>& lag = pw;
   // column accumulation: at[k] = sum_rows A[row,k] L_row(tau), ...
   const uint32_t nv = n_in + n_aux;
   std::vector<hfr::H> acc[3];
-  for (int mi = 0; mi < 3; mi++) {
-    acc[mi].assign(nv, hfr::zero());
-    const hfr::H minus_one = hfr::sub(hfr::zero(), hfr::one());
-    (void)minus_one;
-    for (uint32_t row = 0; row < ng; row++) {
-      const hfr::H& lj = lag[row];
-      for (uint32_t p = csr.rowptr[mi][row]; p < csr.rowptr[mi][row + 1]; p++) {
-        const uint32_t ci = csr.cidx[mi][p];
-        hfr::H& dst = acc[mi][csr.col[mi][p]];
-        if (ci == 0) dst = hfr::add(dst, lj);
-        else if (ci == 1) dst = hfr::sub(dst, lj);
-        else dst = hfr::add(dst, hfr::mul(H_of(csr.coef[ci - 2]), lj));
-      }
-    }
+  {  // the three matrices accumulate into their own arrays: one host thread each
+    std::vector<std::thread> th;
+    for (int mi = 0; mi < 3; mi++)
+      th.emplace_back([&, mi] {
+        acc[mi].assign(nv, hfr::zero());
+        for (uint32_t row = 0; row < ng; row++) {
+          const hfr::H& lj = lag[row];
+          for (uint32_t p = csr.rowptr[mi][row]; p < csr.rowptr[mi][row + 1]; p++) {
+            const uint32_t ci = csr.cidx[mi][p];
+            hfr::H& dst = acc[mi][csr.col[mi][p]];
+            if (ci == 0) dst = hfr::add(dst, lj);
+            else if (ci == 1) dst = hfr::sub(dst, lj);
+            else dst = hfr::add(dst, hfr::mul(H_of(csr.coef[ci - 2]), lj));
+          }
+        }
+      });
+    for (auto& x : th) x.join();
   }
   for (uint32_t i = 0; i < n_in; i++) acc[0][i] = hfr::add(acc[0][i], lag[ng + i]);
   std::vector<Fr> ic_s(n_in), l_s(n_aux), a_s, b_s;
-  for (uint32_t i = 0; i < nv; i++) {
-    hfr::H t = hfr::add(hfr::add(hfr::mul(beta, acc[0][i]), hfr::mul(alpha, acc[1][i])), acc[2][i]);
-    if (i < n_in) ic_s[i] = F_of(hfr::mul(t, ginv));
-    else l_s[i - n_in] = F_of(hfr::mul(t, dinv));
+  host_parallel(nv, [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) {
+      hfr::H t = hfr::add(hfr::add(hfr::mul(beta, acc[0][i]), hfr::mul(alpha, acc[1][i])), acc[2][i]);
+      if (i < n_in) ic_s[i] = F_of(hfr::mul(t, ginv));
+      else l_s[i - n_in] = F_of(hfr::mul(t, dinv));
+    }
+  });
+  for (uint32_t i = 0; i < nv; i++) {  // points at infinity are filtered out of the a / b queries
     if (!hfr::is_zero(acc[0][i])) a_s.push_back(F_of(acc[0][i]));
     if (!hfr::is_zero(acc[1][i])) b_s.push_back(F_of(acc[1][i]));
   }

@@ -31,7 +31,7 @@ class PkInfo(C.Structure):
                 ("len_a", C.c_uint32), ("len_b", C.c_uint32), ("nnz", C.c_uint64),
                 ("hbm_bytes", C.c_uint64), ("g1_digit_slots", C.c_uint64), ("g2_digit_slots", C.c_uint64),
                 ("msm_window_bits", C.c_uint32), ("msm_windows", C.c_uint32), ("msm_tables", C.c_uint32),
-                ("msm_batch_affine", C.c_uint32), ("table_bytes", C.c_uint64)]
+                ("reserved0", C.c_uint32), ("table_bytes", C.c_uint64)]
 
 
 # every symbol declared in include/fawkes_b200.h: (restype, argtypes)
@@ -72,7 +72,6 @@ SIGNATURES = {
     "fb_launch_count": (C.c_uint64, []),
     "fb_set_serial": (None, [C.c_int]),
     "fb_set_msm_tables": (None, [C.c_int]),
-    "fb_set_msm_batch_affine": (None, [C.c_int]),
     "fb_set_prove_graph": (None, [C.c_int]),
     "fb_kernel_stats_enable": (None, [C.c_int]),
     "fb_kernel_stats_reset": (None, []),

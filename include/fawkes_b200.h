@@ -72,7 +72,7 @@ typedef struct fb_pk_info {
   uint32_t msm_window_bits; /* window size chosen for the H MSM */
   uint32_t msm_windows;     /* digits per scalar of the H MSM */
   uint32_t msm_tables;      /* 1 if the key holds the 2^(c w) P window tables */
-  uint32_t msm_batch_affine; /* 1 if the batch-affine rounds are enabled for this key */
+  uint32_t reserved0;       /* was msm_batch_affine (experiment removed in round 2); always 0 */
   uint64_t table_bytes;     /* part of hbm_bytes held by the window tables */
 } fb_pk_info;
 
@@ -205,11 +205,6 @@ void fb_set_serial(int on);
  * -1 auto (default: on when they fit in free HBM with headroom), 0 off, 1 on.  Applies to keys loaded
  * afterwards and to fb_test_msm. */
 void fb_set_msm_tables(int mode);
-/* Batch-affine pre-reduction of the sorted bucket entries (pairwise affine adds sharing one inversion per
- * warp) in front of the XYZZ accumulation: 0 off (default -- exact, but measured slower than the XYZZ
- * kernel on B200), 1 on, 2 on even for small inputs (tests).  Applies to keys loaded
- * afterwards and to fb_test_msm. */
-void fb_set_msm_batch_affine(int on);
 /* Keys with a domain of at most 2^16 replay the device side of a prove as one CUDA graph (captured at the
  * first prove of the key): 1 on (default; FB_PROVE_GRAPH=0 in the environment turns it off), 0 off. */
 void fb_set_prove_graph(int on);

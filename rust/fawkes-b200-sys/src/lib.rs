@@ -55,7 +55,7 @@ pub struct fb_pk_info {
     pub msm_window_bits: u32,
     pub msm_windows: u32,
     pub msm_tables: u32,
-    pub msm_batch_affine: u32,
+    pub reserved0: u32,
     pub table_bytes: u64,
 }
 
@@ -115,6 +115,5 @@ extern "C" {
                      ok: *mut c_int) -> c_int;
     // ---- policy knobs
     pub fn fb_set_msm_tables(mode: c_int);
-    pub fn fb_set_msm_batch_affine(on: c_int);
     pub fn fb_set_prove_graph(on: c_int);
 }

@@ -12,18 +12,14 @@ from tests.util import fr_np, random_g1, random_g2
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[(0, 0), (1, 0), (0, 2), (1, 2)],
-                ids=["plain", "window_tables", "plain+batch_affine", "window_tables+batch_affine"], autouse=True)
+@pytest.fixture(params=[0, 1], ids=["plain", "window_tables"], autouse=True)
 def msm_mode(request):
-    """Every MSM test runs in four modes: plain per-window buckets or the window tables (2^(c w) P, one
-    shared bucket set), each with XYZZ-only accumulation or with the batch-affine rounds forced on (mode 2:
-    also for inputs too small to profit, so the edge cases below go through the pairwise affine adds)."""
+    """Every MSM test runs in both modes: plain per-window buckets, or the window tables (2^(c w) P, one
+    shared bucket set)."""
     import fawkes_crypto_b200 as fb
-    fb.native.lib.fb_set_msm_tables(request.param[0])
-    fb.native.lib.fb_set_msm_batch_affine(request.param[1])
+    fb.native.lib.fb_set_msm_tables(request.param)
     yield request.param
     fb.native.lib.fb_set_msm_tables(-1)
-    fb.native.lib.fb_set_msm_batch_affine(0)
 
 
 def gpu_msm(ctx, group, bases, scalars):

@@ -1,6 +1,8 @@
 // Issue-rate probes for the sm_100a integer pipes and the candidate 256-bit multipliers.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr \
-//        -I fawkes-crypto_b200/csrc tools/pipe_probe.cu -o tools/pipe_probe
+//        -I fawkes-crypto_b200/csrc -I tools/probes tools/pipe_probe.cu -o tools/pipe_probe
+// tools/probes/ff29.cuh and ff52.cuh are the two rejected multipliers this probe measured in round 1 (a carry-free
+// 9 x 29-bit one and an FP64-pipe one, profiles/r01_pipe_probe_*.txt); they are not part of the product.
 // Prints cycles per warp-instruction per SMSP for each stream (from the SM clock) and multiplies/s.
 #include <cstdio>
 #include <cstdlib>

@@ -1,6 +1,6 @@
 """compute-sanitizer target (race / memory checking): one pass through every kernel family at
 small sizes -- field self-test, NTT (strided + contiguous tiles), the H pipeline incl. the virtual-rank distributed
-layout, G1/G2 MSMs with and without window tables and with the batch-affine rounds, GPU gate ingest, setup
+layout, G1/G2 MSMs with and without window tables, GPU gate ingest, setup
 (full and sharded), a plain prove, a CUDA-graph prove, a batched prove (buckets keyed by proof) and verify.
     compute-sanitizer --tool memcheck  python tools/sanitize_target.py
     compute-sanitizer --tool racecheck python tools/sanitize_target.py      (shared-memory hazards: NTT tiles,
@@ -59,18 +59,16 @@ for group, psz in ((1, 64), (2, 128)):
     bases = np.zeros((n, psz), dtype=np.uint8)
     fb.native.check(lib.fb_test_fixed_base(ctx.handle, group, k.ctypes.data, n, bases.ctypes.data))
     ref = None
-    for tables, ba in ((0, 0), (1, 0), (0, 2), (1, 2)):
+    for tables in (0, 1):
         lib.fb_set_msm_tables(tables)
-        lib.fb_set_msm_batch_affine(ba)
         res = np.zeros(psz, dtype=np.uint8)
         fb.native.check(lib.fb_test_msm(ctx.handle, group, bases.ctypes.data, s.ctypes.data, n, res.ctypes.data, 1, None))
         ref = res if ref is None else ref
-        assert np.array_equal(res, ref), ("msm modes differ", group, tables, ba)
+        assert np.array_equal(res, ref), ("msm modes differ", group, tables)
     if group == 1:
         cref, _ = cpu.msm_g1(bases, s, 2)
         assert cref == ref.tobytes(), "G1 MSM differs from the CPU oracle"
 lib.fb_set_msm_tables(-1)
-lib.fb_set_msm_batch_affine(0)
 # circuit -> (sharded) setup -> prove (stream path, graph path, batched path) -> verify; GPU ingest
 seed = 0xFA3CE50000 + 4242
 occ = cpu.Circuit.synthetic(700, seed)
