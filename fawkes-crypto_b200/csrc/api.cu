@@ -1123,7 +1123,7 @@ namespace fb {
 struct BatchWork {
   uint32_t P = 0;
   uint64_t wstride = 0;
-  Fr* w = nullptr;
+  Fr* w[2] = {nullptr, nullptr};   // double buffered: the witness-only MSMs of chunk k+1 run beside chunk k's H pipeline
   Fr* ev[3] = {nullptr, nullptr, nullptr};
   MsmScratch msm[4];
   size_t vmax = 0;                 // V entries per proof per MSM (max over the plans)
@@ -1132,11 +1132,12 @@ struct BatchWork {
   Fr* w_stage[2] = {nullptr, nullptr};
   cudaEvent_t done[2][5];
   cudaEvent_t uploaded[2];
-  cudaEvent_t start = nullptr;
+  cudaEvent_t r1cs_done[2];        // the main stream has finished reading w[q]
+  cudaStream_t up = nullptr;       // witness uploads
   bool used[2] = {false, false};
   bool ok = false;
   void release() {
-    cudaFree(w);
+    for (auto& p : w) cudaFree(p);
     for (auto& p : ev) cudaFree(p);
     for (auto& m : msm) m.release();
     cudaFree(results);
@@ -1145,7 +1146,8 @@ struct BatchWork {
     if (ok) {
       for (auto& q : done) for (auto& e : q) cudaEventDestroy(e);
       for (auto& e : uploaded) cudaEventDestroy(e);
-      cudaEventDestroy(start);
+      for (auto& e : r1cs_done) cudaEventDestroy(e);
+      cudaStreamDestroy(up);
     }
   }
 };
@@ -1161,7 +1163,8 @@ static BatchWork* make_batch(ProvingKey* pk, uint32_t P) {
   const MsmPlan plans[4] = {pk->plan_h.batched(P, pk->m), pk->plan_l.batched(P, b->wstride), pk->plan_a.batched(P, b->wstride),
                             pk->plan_b.batched(P, b->wstride)};
   for (const MsmPlan& p : plans) b->vmax = std::max<size_t>(b->vmax, (size_t)p.vbits_per_set());
-  bool ok = cudaMalloc(&b->w, std::max<size_t>(P * b->wstride, 1) * sizeof(Fr)) == cudaSuccess;
+  bool ok = true;
+  for (int q = 0; q < 2 && ok; q++) ok = cudaMalloc(&b->w[q], std::max<size_t>(P * b->wstride, 1) * sizeof(Fr)) == cudaSuccess;
   for (int i = 0; i < 3 && ok; i++) ok = cudaMalloc(&b->ev[i], (size_t)P * pk->m * sizeof(Fr)) == cudaSuccess;
   for (int i = 0; i < 4 && ok; i++) ok = b->msm[i].alloc(&plans[i], 1, i == 3) == 0;
   const size_t rbytes = 5 * (size_t)P * b->vmax * sizeof(G2XYZZ);
@@ -1173,7 +1176,8 @@ static BatchWork* make_batch(ProvingKey* pk, uint32_t P) {
   if (ok) {
     for (auto& q : b->done) for (auto& e : q) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     for (auto& e : b->uploaded) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&b->start, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : b->r1cs_done) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&b->up, cudaStreamNonBlocking) == cudaSuccess;
     b->ok = true;
   }
   if (!ok) {
@@ -1187,7 +1191,7 @@ static BatchWork* make_batch(ProvingKey* pk, uint32_t P) {
 static int prove_batched(Ctx* ctx, ProvingKey* pk, uint32_t count, const uint64_t* const* inputs, const uint64_t* const* aux,
                          const uint64_t* r, const uint64_t* s, uint8_t* proofs_raw) {
   FB_CUDA(cudaSetDevice(ctx->device));
-  uint32_t P = 128;  // measured on configs[1] (256 proofs): 32 -> 0.28, 64 -> 0.20, 128 -> 0.18, 256 -> 0.20 ms per proof
+  uint32_t P = 64;  // measured on configs[1] (256 proofs, c = 10): 64 -> 0.157, 128 -> 0.163, 256 -> 0.177 ms per proof
   if (const char* e = getenv("FB_BATCH_P")) P = (uint32_t)std::max(1, std::min(1024, atoi(e)));
   P = std::min(P, count);
   BatchWork* bw = reinterpret_cast<BatchWork*>(pk->batch);
@@ -1218,14 +1222,17 @@ static int prove_batched(Ctx* ctx, ProvingKey* pk, uint32_t count, const uint64_
       memcpy(dst, inputs[lo + p], (size_t)pk->n_in * sizeof(Fr));
       if (pk->n_aux) memcpy(dst + pk->n_in, aux[lo + p], (size_t)pk->n_aux * sizeof(Fr));
     }
-    // the witness array is read by the previous chunk's MSMs on the side streams
-    if (k > 0)
-      for (int e = 1; e <= 4; e++) FB_CUDA(cudaStreamWaitEvent(st, bw->done[q ^ 1][e], 0));
-    FB_CUDA(cudaMemcpyAsync(bw->w, bw->w_stage[q], (size_t)cnt * ws * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    FB_CUDA(cudaEventRecord(bw->uploaded[q], st));
+    // w[q] was last read by chunk k-2: its witness-only MSMs on the side streams and its R1CS evaluation
+    Fr* w = bw->w[q];
+    if (k >= 2) {
+      for (int e = 1; e <= 4; e++) FB_CUDA(cudaStreamWaitEvent(bw->up, bw->done[q][e], 0));
+      FB_CUDA(cudaStreamWaitEvent(bw->up, bw->r1cs_done[q], 0));
+    }
+    FB_CUDA(cudaMemcpyAsync(w, bw->w_stage[q], (size_t)cnt * ws * sizeof(Fr), cudaMemcpyHostToDevice, bw->up));
+    FB_CUDA(cudaEventRecord(bw->uploaded[q], bw->up));
     bw->used[q] = true;
-    FB_CUDA(cudaEventRecord(bw->start, st));
-    for (int i = 0; i < 3; i++) FB_CUDA(cudaStreamWaitEvent(ctx->aux[i], bw->start, 0));
+    for (int i = 0; i < 3; i++) FB_CUDA(cudaStreamWaitEvent(ctx->aux[i], bw->uploaded[q], 0));
+    FB_CUDA(cudaStreamWaitEvent(st, bw->uploaded[q], 0));
     const MsmPlan ph = pk->plan_h.batched(cnt, m), pl = pk->plan_l.batched(cnt, ws), pa = pk->plan_a.batched(cnt, ws),
                   pb = pk->plan_b.batched(cnt, ws);
     auto fetch = [&](int slot, size_t bytes, cudaStream_t sx) -> cudaError_t {
@@ -1233,17 +1240,18 @@ static int prove_batched(Ctx* ctx, ProvingKey* pk, uint32_t count, const uint64_
       if (e == cudaSuccess) e = cudaEventRecord(bw->done[q][slot], sx);
       return e;
     };
-    int rc = msm_g2(pk->b2, bw->w, pk->b_map, pb, bw->msm[3], dslot(4), false, sB);
+    int rc = msm_g2(pk->b2, w, pk->b_map, pb, bw->msm[3], dslot(4), false, sB);
     if (!rc) FB_CUDA(fetch(4, sizeof(G2XYZZ) * pb.vbits(), sB));
-    if (!rc) rc = msm_g1(pk->b1, bw->w, pk->b_map, pb, bw->msm[3], (G1XYZZ*)dslot(3), true, sB);
+    if (!rc) rc = msm_g1(pk->b1, w, pk->b_map, pb, bw->msm[3], (G1XYZZ*)dslot(3), true, sB);
     if (!rc) FB_CUDA(fetch(3, sizeof(G1XYZZ) * pb.vbits(), sB));
-    if (!rc) rc = msm_g1(pk->a, bw->w, pk->a_map, pa, bw->msm[2], (G1XYZZ*)dslot(2), false, sA);
+    if (!rc) rc = msm_g1(pk->a, w, pk->a_map, pa, bw->msm[2], (G1XYZZ*)dslot(2), false, sA);
     if (!rc) FB_CUDA(fetch(2, sizeof(G1XYZZ) * pa.vbits(), sA));
-    if (!rc) rc = msm_g1(pk->l, bw->w + pk->n_in, nullptr, pl, bw->msm[1], (G1XYZZ*)dslot(1), false, sL);
+    if (!rc) rc = msm_g1(pk->l, w + pk->n_in, nullptr, pl, bw->msm[1], (G1XYZZ*)dslot(1), false, sL);
     if (!rc) FB_CUDA(fetch(1, sizeof(G1XYZZ) * pl.vbits(), sL));
     if (rc) { set_error("batched MSM launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError())); return FB_ERR_CUDA; }
-    rc = eval_r1cs_batch(pk->csr, bw->w, ws, pk->n_in, bw->ev[0], bw->ev[1], bw->ev[2], m, cnt, st);
+    rc = eval_r1cs_batch(pk->csr, w, ws, pk->n_in, bw->ev[0], bw->ev[1], bw->ev[2], m, cnt, st);
     if (rc) return rc;
+    FB_CUDA(cudaEventRecord(bw->r1cs_done[q], st));
     for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(bw->ev[i], st, cnt, m);
     pk->dom.pointwise_then_icoset_fft(bw->ev[0], bw->ev[1], bw->ev[2], st, cnt, m);
     rc = msm_g1(pk->h, bw->ev[0], nullptr, ph, bw->msm[0], (G1XYZZ*)dslot(0), false, st);

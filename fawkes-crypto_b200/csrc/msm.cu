@@ -52,7 +52,6 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   int tl = 4;
   while (tl < 8 && (1ull << tl) < want) tl++;
   if (tl < MSM_MIN_TASK_LOG) tl = MSM_MIN_TASK_LOG;
-  tl = std::max(tl, p.task_log_for_bucket_size());
   if (const char* e = getenv("FB_MSM_TASK_LOG")) {
     int v = atoi(e);
     if (v >= MSM_MIN_TASK_LOG && v <= 10) tl = v;
@@ -353,6 +352,43 @@ k_bucket_gather(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict
   buckets[b] = acc;
 }
 
+// Latency variant for small problems (a single small prove is a chain of dependent adds, not a throughput problem):
+// one WARP per bucket, the partials strided over the lanes and folded with five shuffle steps, so a bucket with 26
+// partial sums is 6 dependent adds deep instead of 26.  Buckets with more than `heavy_min` partials are queued.
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_down_xyzz(const XYZZ<F>& v, int d) {
+  XYZZ<F> r;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&v);
+  uint32_t* o = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) o[i] = __shfl_down_sync(0xffffffffu, s[i], d);
+  return r;
+}
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_gather_warp(const XYZZ<F>* __restrict__ partials, const uint32_t* __restrict__ offsets, uint32_t nb, int task_log,
+                     uint32_t heavy_min, XYZZ<F>* __restrict__ buckets, uint32_t* __restrict__ heavy) {
+  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= nb) return;  // warp-uniform
+  const uint32_t s = offsets[b], e = offsets[b + 1];
+  if (s == e) { if (lane == 0) buckets[b] = XYZZ<F>::inf(); return; }
+  const uint32_t t0 = s >> task_log, t1 = (e - 1) >> task_log;
+  if (t1 - t0 + 1 > heavy_min) {
+    if (lane == 0) heavy[1 + atomicAdd(&heavy[0], 1u)] = b;
+    return;
+  }
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t t = t0 + lane; t <= t1; t += 32) acc = add_cold(acc, partials[b + t]);
+  if (t1 > t0) {  // warp-uniform: a single partial needs no fold
+#pragma unroll 1
+    for (int d = 16; d > 0; d >>= 1) {
+      const XYZZ<F> o = shfl_down_xyzz(acc, d);
+      acc = add_cold(acc, o);
+    }
+  }
+  if (lane == 0) buckets[b] = acc;
+}
+
 // one CTA per queued bucket: strided partial sums then a shared-memory tree
 template <class F>
 __global__ void __launch_bounds__(MSM_HEAVY_THREADS)
@@ -562,7 +598,10 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   kstat_end(kind, st);
   count_launch(reuse_sort ? 5 : 10);
   kstat_begin(KSTAT_REDUCE, st);
-  k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, offsets, nb, task_log, buckets, s.heavy);
+  if (nb <= MSM_WARP_GATHER_MAX_BUCKETS)
+    k_bucket_gather_warp<F><<<(nb * 32 + 127) / 128, 128, 0, st>>>(partials, offsets, nb, task_log, 32u * MSM_HEAVY, buckets, s.heavy);
+  else
+    k_bucket_gather<F><<<(nb + 127) / 128, 128, 0, st>>>(partials, offsets, nb, task_log, buckets, s.heavy);
   k_bucket_heavy<F><<<148, MSM_HEAVY_THREADS, 0, st>>>(partials, offsets, task_log, s.heavy, buckets);
   const int sbits = p.c - 1 - p.seg_log;  // bits of the segment index within a window
   const uint32_t nsegs = nb >> p.seg_log;

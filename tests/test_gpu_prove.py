@@ -204,6 +204,64 @@ def test_corrupt_gate_stream_is_an_error(ctx):
     assert e.value.code == -3 and "expands beyond" in str(e.value)
 
 
+def test_pageable_witness_takes_the_staged_upload(ctx):
+    """A witness in plain (pageable) host memory -- what a Rust Vec<Num<Fr>> is -- above 4 MiB goes through the
+    library's pinned staging ring (api.cu: upload_host, four copy threads); the proof must equal the one made from
+    pinned memory and from a device-resident witness, and repeated calls must reuse the ring correctly."""
+    import torch
+    import fawkes_crypto_b200 as fb
+    import bench
+    lib = fb.native.lib
+    circ, params, tdi, _ = bench.make_case(fb, ctx, 18)          # 262k aux values = 8.4 MB
+    pk = params.load(ctx, checked=False)
+    wi, wa = circ.witness()
+    n_in, n_aux = wi.shape[0], wa.shape[0]
+    r, s = fb.groth16.fr_raw(tdi[5]), fb.groth16.fr_raw(tdi[6])
+    page = np.empty((n_in + n_aux, 4), dtype=np.uint64)          # pageable
+    page[:n_in], page[n_in:] = wi, wa
+    pinned = torch.empty((n_in + n_aux, 4), dtype=torch.int64).pin_memory()
+    pinned.numpy().view(np.uint64)[:] = page
+    outs = []
+    for src in (page, pinned.numpy().view(np.uint64), page, page):
+        out = np.zeros(256, dtype=np.uint8)
+        fb.native.check(lib.fb_prove(ctx.handle, pk, src.ctypes.data, n_in, src[n_in:].ctypes.data, n_aux, r.ctypes.data,
+                                     s.ctypes.data, out.ctypes.data, None))
+        outs.append(out.tobytes())
+    dev = pinned.cuda()
+    out = np.zeros(256, dtype=np.uint8)
+    fb.native.check(lib.fb_prove_device(ctx.handle, pk, dev.data_ptr(), r.ctypes.data, s.ctypes.data, out.ctypes.data))
+    assert all(o == out.tobytes() for o in outs)
+    assert fb.verify(params.get_vk(), fb.Proof.from_raw(outs[0]), wi[1:])
+    # a different witness in the same pageable buffer must give a different (and still valid) statement: the ring is
+    # not serving stale chunks
+    page[n_in + 5, 0] ^= np.uint64(1)
+    out2 = np.zeros(256, dtype=np.uint8)
+    fb.native.check(lib.fb_prove(ctx.handle, pk, page.ctypes.data, n_in, page[n_in:].ctypes.data, n_aux, r.ctypes.data,
+                                 s.ctypes.data, out2.ctypes.data, None))
+    assert out2.tobytes() != outs[0]
+    params.unload()
+
+
+def test_stream_close_with_queued_proofs_does_not_hang(ctx):
+    """fb_stream_close while proofs are still queued: the ones not started are dropped with an error result, the call
+    returns, and the key is usable afterwards."""
+    import fawkes_crypto_b200 as fb
+    seed = synth.SEED_BASE + 6100
+    gates, inp, aux = synth.synth_circuit(300, seed)
+    td, r0, s0 = synth.synth_trapdoor(seed)
+    P = og.setup(gates, 2, len(aux), td)
+    raw = b"".join(codec.gate_borsh(g) for g in gates)
+    params = fb.Parameters(codec.bellman_params_bytes(P), len(gates), codec.brotli_compress(raw))
+    wi, wa = fr_np(inp), fr_np(aux)
+    st = fb.ProveStream(params, ctx, depth=16)
+    for i in range(16):
+        st.submit(wi, wa, (r0 + i) % bn.R, (s0 + i) % bn.R)
+    st.close()
+    _, proof = fb.groth16.prove_with_rs(params, wi, wa, r0, s0, ctx)
+    assert proof.to_raw() == codec.proof_raw(og.prove(P, gates, inp, aux, r0, s0))
+    params.unload()
+
+
 def test_golden_fixture_through_blob_path(ctx):
     """Committed golden vector (tests/golden, made by tools/gen_golden.py from the oracle): raw
     Parameters bytes + brotli gate blob -> fb_pk_load -> proof bytes."""
