@@ -1409,6 +1409,61 @@ struct ProveStream {
   // faults) and the upload inside the prove is a real asynchronous DMA
   std::vector<uint64_t*> bufs;
   std::vector<int> free_bufs;
+  // small keys: ONE worker takes whatever is queued (up to max_chunk proofs) and proves it as one batched chunk
+  // (prove_batched: one set of launches, buckets keyed by proof) -- the batch size adapts to how fast the caller submits
+  bool batched = false;
+  uint32_t max_chunk = 64;
+
+  void run_batched() {
+    cudaSetDevice(c0->device);
+    for (;;) {
+      std::vector<Job> jobs;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return closing || !queue.empty(); });
+        if (queue.empty()) return;  // closing
+        while (!queue.empty() && jobs.size() < max_chunk) {
+          jobs.push_back(queue.front());
+          queue.pop_front();
+        }
+      }
+      const size_t n = jobs.size();
+      std::vector<Result> res(n);
+      if (n == 1) {
+        const uint64_t* w = bufs[jobs[0].buf];
+        res[0].rc = prove_impl(c0, pk, w, pk->n_in, pk->n_aux ? w + 4 * (size_t)pk->n_in : nullptr, pk->n_aux, nullptr,
+                               jobs[0].r, jobs[0].s, res[0].proof, nullptr, nullptr);
+        if (res[0].rc) res[0].err = last_error_cstr();
+      } else {
+        std::vector<const uint64_t*> ins(n), axs(n);
+        std::vector<uint64_t> rr(4 * n), ss(4 * n);
+        std::vector<uint8_t> proofs(256 * n);
+        for (size_t i = 0; i < n; i++) {
+          ins[i] = bufs[jobs[i].buf];
+          axs[i] = ins[i] + 4 * (size_t)pk->n_in;
+          memcpy(&rr[4 * i], jobs[i].r, 32);
+          memcpy(&ss[4 * i], jobs[i].s, 32);
+        }
+        const int rc = prove_batched(c0, pk, (uint32_t)n, ins.data(), axs.data(), rr.data(), ss.data(), proofs.data());
+        const std::string err = rc ? last_error_cstr() : "";
+        for (size_t i = 0; i < n; i++) {
+          res[i].rc = rc;
+          res[i].err = err;
+          memcpy(res[i].proof, &proofs[256 * i], 256);
+        }
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < n; i++) {
+          done.emplace(jobs[i].ticket, std::move(res[i]));
+          free_bufs.push_back(jobs[i].buf);
+          in_flight--;
+        }
+      }
+      cv_done.notify_all();
+      cv_space.notify_all();
+    }
+  }
 
   void run(int t) {
     ProvingKey* p = t == 0 ? pk : pk->slots[t - 1];
@@ -1449,6 +1504,11 @@ int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
   if (const char* e = getenv("FB_BATCH_SLOTS")) want = std::max(1, std::min(32, atoi(e)));
   if (pk->m > (1u << 16) || g_serial) want = 1;  // a big prove fills the GPU on its own (fb_prove_batch)
   FB_CUDA(cudaSetDevice(c0->device));
+  const char* mode = getenv("FB_BATCH_MODE");
+  const bool batched = pk->m <= (1u << 16) && !g_serial && !(mode && !strcmp(mode, "slots"));
+  uint32_t max_chunk = 64;
+  if (const char* e = getenv("FB_BATCH_P")) max_chunk = (uint32_t)std::max(1, std::min(1024, atoi(e)));
+  if (batched) want = 1;  // one worker, batched chunks
   while ((int)pk->slots.size() + 1 < want) {
     ProvingKey* sl = make_slot(pk);
     if (!sl) break;
@@ -1458,7 +1518,9 @@ int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
   ProveStream* st = new ProveStream();
   st->c0 = c0;
   st->pk = pk;
-  st->depth = (size_t)std::max(depth > 0 ? depth : 2 * K, 1);
+  st->batched = batched;
+  st->max_chunk = max_chunk;
+  st->depth = (size_t)std::max(depth > 0 ? depth : (batched ? 2 * (int)max_chunk : 2 * K), 1);
   const size_t wbytes = std::max<size_t>(((size_t)pk->n_in + pk->n_aux) * sizeof(Fr), 32);
   for (size_t i = 0; i < st->depth; i++) {
     void* b = nullptr;
@@ -1472,7 +1534,8 @@ int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
     st->bufs.push_back(reinterpret_cast<uint64_t*>(b));
     st->free_bufs.push_back((int)i);
   }
-  for (int t = 0; t < K; t++) st->workers.emplace_back([st, t] { st->run(t); });
+  if (batched) st->workers.emplace_back([st] { st->run_batched(); });
+  else for (int t = 0; t < K; t++) st->workers.emplace_back([st, t] { st->run(t); });
   *out = reinterpret_cast<fb_stream*>(st);
   return FB_OK;
 }

@@ -91,6 +91,35 @@ def test_msm_linearity_large(ctx):
     assert codec.g1_unraw(out.tobytes()) == bn.pt_mul(bn.OPS1, bn.G1_GEN, tot % bn.R)
 
 
+def test_msm_skewed_large(ctx):
+    """2^17 points with a real-witness-like scalar distribution: 40 % ones, 10 % twos, 10 % zeros, a few r-1, the rest
+    random.  One bucket then holds tens of thousands of entries: equal-length tasks spread it over hundreds of threads and
+    the heavy-bucket path (k_bucket_heavy: a CTA per bucket, strided sums + tree) folds its partial sums.  Checked with
+    the scalar identity MSM(s) == (sum s_i k_i) * G on bases k_i * G."""
+    import fawkes_crypto_b200 as fb
+    n = 1 << 17
+    rng = np.random.default_rng(23)
+    k = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    k[:, 3] &= np.uint64((1 << 60) - 1)
+    s = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    s[:, 3] &= np.uint64((1 << 60) - 1)
+    kind = rng.random(n)
+    one, two, rm1 = fr_np([1])[0], fr_np([2])[0], fr_np([bn.R - 1])[0]
+    s[kind < 0.4] = one
+    s[(kind >= 0.4) & (kind < 0.5)] = two
+    s[(kind >= 0.5) & (kind < 0.6)] = 0
+    s[(kind >= 0.6) & (kind < 0.601)] = rm1
+    bases = np.zeros((n, 64), dtype=np.uint8)
+    fb.native.check(fb.native.lib.fb_test_fixed_base(ctx.handle, 1, k.ctypes.data, n, bases.ctypes.data))
+    out = np.zeros(64, dtype=np.uint8)
+    fb.native.check(fb.native.lib.fb_test_msm(ctx.handle, 1, bases.ctypes.data, s.ctypes.data, n, out.ctypes.data, 1, None))
+    kb, sb = k.tobytes(), s.tobytes()
+    tot = 0
+    for i in range(n):
+        tot += codec.fr_unraw(kb[32 * i:32 * i + 32]) * codec.fr_unraw(sb[32 * i:32 * i + 32])
+    assert codec.g1_unraw(out.tobytes()) == bn.pt_mul(bn.OPS1, bn.G1_GEN, tot % bn.R)
+
+
 @pytest.mark.parametrize("group", [1, 2])
 def test_fixed_base(ctx, group):
     import fawkes_crypto_b200 as fb
