@@ -17,19 +17,21 @@ MsmPlan MsmPlan::make(uint32_t n, bool table) {
   while ((2u << lg) <= n && lg < 31) lg++;
   int c;
   if (table) {
-    // One bucket set for all windows: n*W mixed adds to accumulate, and sort + reduction work per bucket
-    // worth ~20 mixed adds (measured: 2^24 rows c = 20 beats 22 by 9 ms, 2^20 rows c = 17 beats 19 by
-    // 1.5 ms; profiles/r01_window_sweep.txt).  Windows whose top digit has only a few bits are skipped WHEN n is
-    // large: all n top digits then land in a handful of buckets, tens of thousands of atomics per counter in the
-    // digit sort (c = 21 / 23 at 2^24 cost +30 / +70 ms).  Small circuits keep them: at n = 8191 the rule left only
-    // c = 8 (32 digits per scalar, every bucket "heavy") where c = 10 needs 26 (profiles/r02_cfg2_batch_launches.csv).
+    // One bucket set for all windows: n*W mixed adds to accumulate, and sort + reduction work per bucket worth ~15
+    // mixed adds (2 ns per bucket against 0.135 ns per add; measured sweeps: profiles/r01_window_sweep.txt, and this
+    // round profiles/r02_window_sweep_2e21.txt, r02_window_sweep_2e22.txt: 2^22 points c = 17 / 19 / 20 -> 66.5 / 69.0 /
+    // 63.5 ms).  Windows whose top digit has only a few bits are skipped: all n top digits then land in a handful of
+    // buckets, thousands of atomics per counter in the digit sort (c = 21 / 23 at 2^24 cost +30 / +70 ms; c = 19 at
+    // 2^22 doubles the sort).  Small circuits (at most 4096 entries per top bucket, at least 3 top bits) keep them: at
+    // n = 8191 the rule left only c = 8 -- 32 digits per scalar, every bucket "heavy" -- where c = 10 needs 26
+    // (profiles/r02_small_circuit_window_sweep.txt).
     double best = 1e300;
     c = 0;
     for (int cand = std::max(4, lg - 6); cand <= std::min(22, std::max(4, lg)); cand++) {
       const int Wc = (255 + cand - 1) / cand;
       const int top_bits = 254 - (Wc - 1) * cand;
-      if (2 * top_bits < cand && (n >> std::max(top_bits, 0)) > 65536u) continue;
-      const double cost = (double)n * Wc + 20.0 * (double)(1u << (cand - 1));
+      if (2 * top_bits < cand && (top_bits < 3 || (n >> top_bits) > 4096u)) continue;
+      const double cost = (double)n * Wc + 15.0 * (double)(1u << (cand - 1));
       if (cost < best) { best = cost; c = cand; }
     }
     if (c == 0) c = std::max(4, std::min(22, lg - 3));
