@@ -416,6 +416,16 @@ int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, doubl
   return FB_OK;
 }
 
+// Host only: the Pippenger plan MsmPlan::make picks for n points (window bits, digits per scalar, log2 entries per
+// accumulation task) with or without window tables -- lets the CPU tests pin the plans of the benchmark sizes.
+int fb_test_msm_plan(uint32_t n, int table, int* c, int* W, int* task_log) {
+  const MsmPlan p = MsmPlan::make(n, table != 0);
+  if (c) *c = p.c;
+  if (W) *W = p.W;
+  if (task_log) *task_log = p.task_log;
+  return FB_OK;
+}
+
 int fb_probe_fr_mul(fb_ctx* ctx_, double* mul_per_s) {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !mul_per_s) return FB_ERR_ARG;

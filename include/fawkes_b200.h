@@ -226,6 +226,8 @@ int fb_test_dist_h(fb_ctx* ctx, int log_n, int g, const uint64_t* a, const uint6
 /* MSM on host buffers: group 1 (bases 64 B) or 2 (128 B); result raw affine; reps>1 times it */
 int fb_test_msm(fb_ctx* ctx, int group, const uint8_t* bases_raw, const uint64_t* scalars,
                 uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep);
+/* host only: window bits, digits per scalar and log2(entries per accumulation task) MsmPlan::make picks for n points */
+int fb_test_msm_plan(uint32_t n, int table, int* c, int* W, int* task_log);
 /* bases[i] = k_i * G (fixed-base kernel used by setup), raw affine out */
 int fb_test_fixed_base(fb_ctx* ctx, int group, const uint64_t* scalars, uint64_t n,
                        uint8_t* out_raw);

@@ -169,6 +169,30 @@ def test_host_verify_and_framing_on_golden(golden):
     assert e.value.code == -7
 
 
+def test_msm_window_plans_of_the_benchmark_sizes():
+    """MsmPlan::make (host logic): the windows DESIGN.md section 4.4 quotes for the benchmark sizes, with window tables.
+    n: points of one MSM (a whole key, or one rank's shard of it)."""
+    import fawkes_crypto_b200 as fb
+
+    def plan(n, table=1):
+        c, W, tl = C.c_int(), C.c_int(), C.c_int()
+        fb.native.check(fb.native.lib.fb_test_msm_plan(n, table, C.byref(c), C.byref(W), C.byref(tl)))
+        assert W.value * c.value >= 255 and (W.value - 1) * c.value < 255      # digits cover the scalar, no spare window
+        return c.value, W.value
+
+    assert plan(1 << 24) == (20, 13)            # configs[3] on one GPU
+    assert plan(1 << 23) == (20, 13)            # ... its 2-GPU shards
+    assert plan(1 << 22) == (20, 13)            # ... 4-GPU shards (c = 19 would pile 2^22 top digits on 128 counters)
+    assert plan(1 << 21) == (17, 15)            # ... 8-GPU shards
+    assert plan(1 << 20) == (17, 15)            # configs[2]
+    assert plan(35695616 // 8) == (20, 13)      # configs[4] l/a/b shards on 8 GPUs
+    assert plan(8191) == (10, 26) and plan(4125) == (10, 26)     # configs[0] / [1]: small circuits keep a 4-bit top digit
+    for n in (1, 2, 3, 100, 5000, 1 << 16, (1 << 26) - 1):
+        for table in (0, 1):
+            c, W = plan(n, table)
+            assert 4 <= c <= 22
+
+
 def g2_point_outside_the_subgroup(seed=1):
     """A point of the twist curve y^2 = x^3 + 3/(9+u) that is NOT in the r-torsion subgroup (the cofactor of
     BN254's G2 is ~2^254, so the first curve point found by trying x values is outside)."""
