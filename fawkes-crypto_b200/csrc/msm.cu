@@ -440,6 +440,42 @@ k_bucket_segments(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, int seg_l
   segS[s] = run;
 }
 
+// Latency variant for at most MSM_COOP_SEGMENTS_MAX segments (a single small prove: configs[0] 1.6 -> 1.3 ms):
+// EIGHT lanes per segment of 8 buckets.  Suffix sums run_t = sum_{j >= t} B_j by three shuffle steps,
+// then R = sum_t run_t (every B_j is counted j + 1 times) by three more, S = run_0: 6 dependent adds instead of 16,
+// for 3x the lane-adds -- these launches are far too small to be throughput-bound.
+template <class F>
+__global__ void __launch_bounds__(128)
+k_bucket_segments_coop(const XYZZ<F>* __restrict__ buckets, uint32_t nsegs, XYZZ<F>* __restrict__ segR,
+                       XYZZ<F>* __restrict__ segS) {
+  const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t s = gid >> 3, t = gid & 7;
+  XYZZ<F> run = s < nsegs ? buckets[((uint64_t)s << 3) + t] : XYZZ<F>::inf();
+#pragma unroll 1
+  for (int d = 1; d < 8; d <<= 1) {
+    XYZZ<F> o;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&run);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, 8);
+    if (t + d < 8) run = add_cold(run, o);
+  }
+  XYZZ<F> tot = run;
+#pragma unroll 1
+  for (int d = 4; d > 0; d >>= 1) {
+    XYZZ<F> o;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&tot);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(XYZZ<F>) / 4); i++) dst[i] = __shfl_down_sync(0xffffffffu, src[i], d, 8);
+    if (t < (uint32_t)d) tot = add_cold(tot, o);
+  }
+  if (t == 0 && s < nsegs) {
+    segR[s] = tot;
+    segS[s] = run;
+  }
+}
+
 // grid = wred * (1 + sbits) * parts CTAs, sbits = bits of the segment index.  Job (w, 0): V[c w] = sum_s R_s;
 // job (w, 1 + k): V[c w + seg_log + k] = sum of S_s over segments whose index has bit k set.  A job's
 // segment range is cut into `parts` CTAs (window-table plans have one window of up to 2^18 segments);
@@ -612,7 +648,10 @@ static int msm_run(const Affine<F>* bases, const Fr* scalars, const uint32_t* ma
   const int parts = bits_parts(p);
   const int jobs = p.wred() * (1 + sbits);
   cudaMemsetAsync(V, 0, sizeof(XYZZ<F>) * vcount, st);
-  k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
+  if (p.seg_log == 3 && nsegs <= MSM_COOP_SEGMENTS_MAX)
+    k_bucket_segments_coop<F><<<(nsegs * 8 + 127) / 128, 128, 0, st>>>(buckets, nsegs, segR, segS);
+  else
+    k_bucket_segments<F><<<(nsegs + 127) / 128, 128, 0, st>>>(buckets, nsegs, p.seg_log, segR, segS);
   k_segment_bits<F, BT><<<jobs * parts, BT, 0, st>>>(segR, segS, p.c, p.seg_log, sbits, parts, V,
                                                     reinterpret_cast<XYZZ<F>*>(s.winsum));
   if (parts > 1) {

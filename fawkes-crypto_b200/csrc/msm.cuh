@@ -31,6 +31,7 @@ constexpr int MSM_MIN_TASK_LOG = 4;
 constexpr uint32_t MSM_MIN_TASK = 1u << MSM_MIN_TASK_LOG;
 constexpr uint32_t MSM_HEAVY = 32;        // partials per bucket handled by one thread
 constexpr int MSM_HEAVY_THREADS = 128;
+constexpr uint32_t MSM_COOP_SEGMENTS_MAX = 1024;   // up to here the segment sums use eight lanes per segment (latency path; measured: no gain at 4096-8192 segments, where the launch is work-bound)
 constexpr uint32_t MSM_WARP_GATHER_MAX_BUCKETS = 4096;  // up to here buckets are folded by a warp each (latency path; measured: at 32 k buckets it already costs a batched prove +35 %)
 constexpr int MSM_VBITS = 288;            // >= W*c for every plan (255 + c - 1 <= 274 for c <= 20)
 
