@@ -131,7 +131,10 @@ int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, cons
              uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
              uint64_t* h_out);
 /* `count` proofs on one resident key (BASELINE configs[1]: 256 eddsa proofs per run): inputs[i],
- * aux[i] as for fb_prove; r, s: [count][4]; proofs_raw: [count][256]. */
+ * aux[i] as for fb_prove; r, s: [count][4]; proofs_raw: [count][256].  Keys with a domain of at most 2^16 are proved
+ * in chunks of FB_BATCH_P (default 64) proofs with one set of launches per chunk: the proof index is a grid dimension of
+ * R1CS evaluation and transforms, and the five MSMs are batched MSMs whose buckets are keyed by (proof, digit).
+ * Byte-identical to fb_prove one proof at a time. */
 int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
                    const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
                    uint8_t* proofs_raw);
@@ -140,7 +143,9 @@ int fb_prove_batch(fb_ctx* ctx, fb_pk* pk, uint32_t count, const uint64_t* const
  * and returns (it blocks only while `depth` proofs are already queued or running; depth <= 0 picks a default),
  * so witness k+1 is generated while proof k runs.  wait blocks until that proof is done and hands out the
  * same bytes fb_prove would; tickets may be collected in any order, each once.  While a stream is open the
- * key must be used through it only.  close drops proofs that have not started. */
+ * key must be used through it only.  close drops proofs that have not started (their tickets complete with an
+ * error).  Keys with a domain of at most 2^16 prove whatever is queued as ONE batched chunk (see fb_prove_batch), so
+ * the batch size follows the caller's submission rate. */
 typedef struct fb_stream fb_stream;
 int fb_stream_open(fb_ctx* ctx, fb_pk* pk, int depth, fb_stream** out);
 int fb_stream_submit(fb_stream* st, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux, uint32_t n_aux,
