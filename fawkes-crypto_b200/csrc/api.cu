@@ -499,7 +499,8 @@ static inline G2XYZZ* vslot(void* base, int i) { return reinterpret_cast<G2XYZZ*
 
 // device part: w already in pk->w (on the main stream).  Every MSM leaves its bit sums in
 // pk->results_host and records an event on its stream.  NOT synchronised on return.
-static int prove_launch(ProvingKey* pk, uint64_t* h_out) {
+static int prove_launch(ProvingKey* pk, uint64_t* h_out, const Fr* w = nullptr) {
+  if (!w) w = pk->w;  // fb_prove_device: the caller's device buffer is read in place, no copy
   Ctx* ctx = pk->ctx;
   cudaStream_t st = ctx->stream;
   cudaStream_t sL = g_serial ? st : ctx->aux[0], sA = g_serial ? st : ctx->aux[1],
@@ -520,13 +521,13 @@ static int prove_launch(ProvingKey* pk, uint64_t* h_out) {
     return e;
   };
   // witness-only MSMs start at once on their own streams; the G2 one first (longest)
-  int rc = msm_g2(pk->b2, pk->w, pk->b_map, pk->plan_b, pk->msm[3], vslot(pk->results, 4), false, sB);
+  int rc = msm_g2(pk->b2, w, pk->b_map, pk->plan_b, pk->msm[3], vslot(pk->results, 4), false, sB);
   if (!rc) FB_CUDA(fetch(4, sizeof(G2XYZZ) * MSM_VBITS, sB, 4));
-  if (!rc) rc = msm_g1(pk->b1, pk->w, pk->b_map, pk->plan_b, pk->msm[3], (G1XYZZ*)vslot(pk->results, 3), true, sB);
+  if (!rc) rc = msm_g1(pk->b1, w, pk->b_map, pk->plan_b, pk->msm[3], (G1XYZZ*)vslot(pk->results, 3), true, sB);
   if (!rc) FB_CUDA(fetch(3, sizeof(G1XYZZ) * MSM_VBITS, sB, 3));
-  if (!rc) rc = msm_g1(pk->a, pk->w, pk->a_map, pk->plan_a, pk->msm[2], (G1XYZZ*)vslot(pk->results, 2), false, sA);
+  if (!rc) rc = msm_g1(pk->a, w, pk->a_map, pk->plan_a, pk->msm[2], (G1XYZZ*)vslot(pk->results, 2), false, sA);
   if (!rc) FB_CUDA(fetch(2, sizeof(G1XYZZ) * MSM_VBITS, sA, 2));
-  if (!rc) rc = msm_g1(pk->l, pk->w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)vslot(pk->results, 1), false, sL);
+  if (!rc) rc = msm_g1(pk->l, w + pk->n_in + l_lo, nullptr, pk->plan_l, pk->msm[1], (G1XYZZ*)vslot(pk->results, 1), false, sL);
   if (!rc) FB_CUDA(fetch(1, sizeof(G1XYZZ) * MSM_VBITS, sL, 1));
   // R1CS evaluation and the H pipeline on the main stream
   if (rc) {
@@ -535,14 +536,14 @@ static int prove_launch(ProvingKey* pk, uint64_t* h_out) {
   }
   if (pk->dist_g) {
     if (h_out) { set_error("h_out is not available on a distributed key"); return FB_ERR_ARG; }
-    rc = eval_r1cs_cyclic(pk->csr, pk->w, pk->n_in, pk->n_gates_global, pk->dist_g, pk->shard, pk->ev[0], pk->ev[1],
+    rc = eval_r1cs_cyclic(pk->csr, w, pk->n_in, pk->n_gates_global, pk->dist_g, pk->shard, pk->ev[0], pk->ev[1],
                           pk->ev[2], m >> pk->dist_g, st);
     if (rc) return rc;
     cudaEventRecord(T.ev[2], st);
     rc = pk->dom.dist_h_pipeline(pk->ev, pk->xtmp, pk->dist_g, pk->shard, dist_exchange(ctx), st);
     if (rc) { if (rc != FB_ERR_CUDA) set_error("distributed H pipeline failed (%d)", rc); return FB_ERR_CUDA; }
   } else {
-    rc = eval_r1cs(pk->csr, pk->w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
+    rc = eval_r1cs(pk->csr, w, pk->n_in, pk->ev[0], pk->ev[1], pk->ev[2], m, st);
     if (rc) return rc;
     cudaEventRecord(T.ev[2], st);
     for (int i = 0; i < 3; i++) pk->dom.ifft_then_coset_fft(pk->ev[i], st);
@@ -736,8 +737,8 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
   }
   cudaEventRecord(g_timing.ev[0], st);
   if (dev_w) {
-    FB_CUDA(cudaMemcpyAsync(pk->w, dev_w, (size_t)(pk->n_in + pk->n_aux) * sizeof(Fr),
-                            cudaMemcpyDeviceToDevice, st));
+    // the witness is already in HBM: every kernel of the prove reads the caller's buffer in place (the call is
+    // synchronous, so the buffer outlives them); a 512 MiB device-to-device copy would cost 0.3 ms per prove
   } else if (ctx->exchange && ctx->world == pk->nshards && pk->nshards > 1 && ctx->rank == pk->shard) {
     // every rank uploads 1/world of the witness over its own PCIe link, NVLink all-gathers the rest
     const uint64_t total = (uint64_t)n_in + n_aux, W = pk->nshards;
@@ -758,7 +759,7 @@ static int prove_impl(Ctx* ctx, ProvingKey* pk, const uint64_t* inputs, uint32_t
     if (urc) return urc;
   }
   auto tl0 = std::chrono::steady_clock::now();
-  int rc = prove_launch(pk, h_out);
+  int rc = prove_launch(pk, h_out, reinterpret_cast<const Fr*>(dev_w));
   if (rc) { cudaDeviceSynchronize(); return rc; }
   auto tl1 = std::chrono::steady_clock::now();
   // host work that needs only r, s and the key overlaps the device
@@ -1056,7 +1057,10 @@ static int prove_collective(Ctx* ctx, ProvingKey* p, const uint64_t* inputs, uin
   VkPoints vk{p->alpha_g1, p->beta_g1, p->delta_g1, p->beta_g2, p->delta_g2};
   rc = fixed_terms(&vk, reinterpret_cast<const KeyTables*>(p->host_tables), r, s, ft);
   if (rc) return rc;
-  finish_proof(ft, sum[0], sum[1], sum[2], sum[3], sum2, nullptr, nullptr, proof_raw);
+  auto fut_rb1 = std::async(std::launch::async, [&]() -> H1 { return scalar_mul(sum[3], ft.rc); });
+  const H1 sA = scalar_mul(sum[2], ft.sc);
+  const H1 rB1 = fut_rb1.get();
+  finish_proof(ft, sum[0], sum[1], sum[2], sum[3], sum2, &sA, &rB1, proof_raw);
   const double combine_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   g_timing.ms[4] += (float)combine_ms;
   g_timing.ms[5] += (float)combine_ms;

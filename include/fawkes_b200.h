@@ -152,7 +152,8 @@ int fb_stream_submit(fb_stream* st, const uint64_t* inputs, uint32_t n_in, const
                      const uint64_t r[4], const uint64_t s[4], uint64_t* ticket);
 int fb_stream_wait(fb_stream* st, uint64_t ticket, uint8_t proof_raw[256]);
 void fb_stream_close(fb_stream* st);
-/* Same, host buffers already on the device (dev_w = [inputs | aux] as Num<Fr>). */
+/* Same, witness already on the device: dev_w = [inputs | aux] as Num<Fr>, 16-byte aligned, READ IN PLACE by the kernels
+ * of the prove (no copy): it must stay unchanged until the call returns. */
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
                     const uint64_t s[4], uint8_t proof_raw[256]);
 /* Sharded prove: partial[5] raw affine sums in the order h, l, a, b_g1 (64 B each, slots of
