@@ -60,6 +60,11 @@ struct NcclExchange : NttExchange {
   // combine step of a sharded prove: world x 640-byte partial sums (device + pinned host mirror)
   uint8_t* gather_dev = nullptr;
   uint8_t* gather_host = nullptr;
+  // exchanges of one array overlap the transforms of the next (ntt.cu: dist_h_pipeline)
+  cudaStream_t side = nullptr;
+  cudaEvent_t evs[12] = {};
+  cudaStream_t side_stream() override { return side; }
+  cudaEvent_t event(int i) override { return evs[i]; }
   int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count, cudaStream_t st) override {
     NcclApi& n = nccl();
     int rc = n.GroupStart();
@@ -121,6 +126,8 @@ void dist_destroy(Ctx* ctx) {
   if (!x) return;
   if (x->gather_dev) cudaFree(x->gather_dev);
   if (x->gather_host) cudaFreeHost(x->gather_host);
+  if (x->side) cudaStreamDestroy(x->side);
+  for (auto& e : x->evs) if (e) cudaEventDestroy(e);
   NcclApi& n = nccl();
   if (x->comm && n.CommDestroy) n.CommDestroy(x->comm);
   delete x;
@@ -192,6 +199,11 @@ int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) {
   x->world = world;
   int rc = n.CommInitRank(&x->comm, world, u, rank);
   if (rc) { set_error("ncclCommInitRank: %s", n.GetErrorString(rc)); delete x; return FB_ERR_CUDA; }
+  if (!getenv("FB_DIST_NO_OVERLAP")) {  // without the side stream the exchanges run on the compute stream
+    bool ok = cudaStreamCreateWithFlags(&x->side, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : x->evs) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); if (x->side) cudaStreamDestroy(x->side); x->side = nullptr; }
+  }
   if (ctx->exchange) dist_destroy(ctx);
   ctx->exchange = x;
   ctx->rank = rank;

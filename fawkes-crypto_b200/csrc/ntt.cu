@@ -417,6 +417,49 @@ int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int ran
   dist_plan(g, &np, lb, b);
   const NttShard cyc{g, (uint32_t)rank}, blk{0, 0};
   Fr z = Fr::zero();
+  cudaStream_t cs = xch->side_stream();
+  int rc = 0;
+  if (cs) {
+    // Overlapped schedule: the exchange of one array runs on the side stream while the compute stream transforms
+    // the next one (every rank issues the exchanges in the same order: a, b, c, then a, b, c).
+    auto ev_ = [&](int i) { return xch->event(i); };
+    // 1 + 2. cyclic inverse DIF on the high bits, then cyclic -> block, array by array
+    for (int v = 0; v < 3; v++) {
+      for (int i = np - 1; i >= 0; i--)
+        launch_pass<0, true>(ev[v], nullptr, nullptr, tab_plain, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+      cudaEventRecord(ev_(v), st);
+      cudaStreamWaitEvent(cs, ev_(v), 0);
+      const Fr* send1[1] = {ev[v]};
+      Fr* recv1[1] = {tmp[v]};
+      kstat_begin(KSTAT_EXCHANGE, cs);
+      rc = xch->all_to_all(send1, recv1, 1, C, cs);
+      if (rc) return rc;
+      kstat_end(KSTAT_EXCHANGE, cs);
+      cudaEventRecord(ev_(3 + v), cs);
+    }
+    // 3 + 4. block layout: last bm inverse stages + first bm forward (coset) stages in one tile, then block -> cyclic
+    for (int v = 0; v < 3; v++) {
+      cudaStreamWaitEvent(st, ev_(3 + v), 0);
+      k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[v], tmp[v], g, C);
+      launch_pass<2, true>(ev[v], nullptr, nullptr, tab_plain, tab_coset, k, 0, bm, z, z, st, kl, blk);
+      k_pack_from_block<<<grid_for(ml), 256, 0, st>>>(tmp[v], ev[v], g, C);
+      cudaEventRecord(ev_(6 + v), st);
+      cudaStreamWaitEvent(cs, ev_(6 + v), 0);
+      const Fr* send1[1] = {tmp[v]};
+      Fr* recv1[1] = {ev[v]};
+      kstat_begin(KSTAT_EXCHANGE, cs);
+      rc = xch->all_to_all(send1, recv1, 1, C, cs);
+      if (rc) return rc;
+      kstat_end(KSTAT_EXCHANGE, cs);
+      cudaEventRecord(ev_(9 + v), cs);
+    }
+    // 5. cyclic forward (coset) DIT on the high bits
+    for (int v = 0; v < 3; v++) {
+      cudaStreamWaitEvent(st, ev_(9 + v), 0);
+      for (int i = 0; i < np; i++)
+        launch_pass<1, false>(ev[v], nullptr, nullptr, tab_coset, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+    }
+  } else {
   // 1. cyclic inverse DIF on the high bits (three arrays)
   for (int v = 0; v < 3; v++)
     for (int i = np - 1; i >= 0; i--)
@@ -424,7 +467,7 @@ int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int ran
   // 2. cyclic -> block: contiguous chunks out, strided placement in
   const Fr* send3[3] = {ev[0], ev[1], ev[2]};
   kstat_begin(KSTAT_EXCHANGE, st);
-  int rc = xch->all_to_all(send3, tmp, 3, C, st);
+  rc = xch->all_to_all(send3, tmp, 3, C, st);
   if (rc) return rc;
   for (int v = 0; v < 3; v++) k_unpack_to_block<<<grid_for(ml), 256, 0, st>>>(ev[v], tmp[v], g, C);
   kstat_end(KSTAT_EXCHANGE, st);
@@ -442,6 +485,7 @@ int NttDomain::dist_h_pipeline(Fr* const ev[3], Fr* const tmp[3], int g, int ran
   for (int v = 0; v < 3; v++)
     for (int i = 0; i < np; i++)
       launch_pass<1, false>(ev[v], nullptr, nullptr, tab_coset, nullptr, k, lb[i], b[i], z, z, st, kl, cyc);
+  }
   // 6. pointwise + cyclic inverse-coset DIF on the high bits
   for (int i = np - 1; i >= 0; i--) {
     if (i == np - 1)

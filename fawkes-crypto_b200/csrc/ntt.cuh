@@ -21,6 +21,10 @@ struct NttExchange {
   virtual ~NttExchange() {}
   virtual int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count,
                          cudaStream_t st) = 0;
+  // A second stream (+ events) on which exchanges may run beside the transforms of the other arrays; nullptr =
+  // the transport wants everything on the compute stream (the single-process test stand-in).
+  virtual cudaStream_t side_stream() { return nullptr; }
+  virtual cudaEvent_t event(int i) { (void)i; return nullptr; }   // i in [0, 12)
 };
 
 struct NttDomain {
