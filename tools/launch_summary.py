@@ -16,7 +16,9 @@ rows = rows[1:]
 if "--last-prove" in sys.argv:
     # a prove = everything between two h2d-separated groups; we split on the witness MSM's first k_digits<0>
     # that follows a k_fold_parts/k_segment_bits of the H MSM, i.e. on groups of 3 consecutive k_spmv
-    spmv = [i for i, r in enumerate(rows) if r[ki].startswith("k_spmv")]
+    # only the library's prove kernels (no torch fill kernels of the L2 flush, no pipe probe after the last prove)
+    rows = [r for r in rows if "fb::" in r[ki] and "k_probe" not in r[ki]] or rows
+    spmv = [i for i, r in enumerate(rows) if "k_spmv" in r[ki].split("(")[0]]
     groups = [spmv[i] for i in range(0, len(spmv), 3)]
     if len(groups) >= 2:
         per = groups[-1] - groups[-2]
@@ -26,7 +28,7 @@ if "--last-prove" in sys.argv:
 agg = collections.OrderedDict()
 tot = 0.0
 for r in rows:
-    k = r[ki][:70]
+    k = r[ki].replace("fb::", "")[:70]
     v = float(r[vi].replace(",", ""))
     agg.setdefault(k, [0, 0.0])
     agg[k][0] += 1
