@@ -1327,9 +1327,10 @@ int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* cons
                    uint8_t* proofs_raw) {
   if (!inputs || (!aux && n_aux) || !r || !s || !proofs_raw) { set_error("fb_prove_batch: null buffer"); return FB_ERR_ARG; }
   // The reference proves one circuit per prove() call (prover.rs:63-90); a batch is the same key used
-  // `count` times.  The proofs are independent and a small prove is a chain of ~70 tiny launches that
-  // leaves the GPU idle, so up to FB_BATCH_SLOTS (default 8) of them are kept in flight: one host thread
-  // and one set of streams and workspaces per slot, all reading the same resident key.
+  // `count` times.  Small keys (domain <= 2^16) go through prove_batched above: one set of launches per chunk of
+  // proofs.  FB_BATCH_MODE=slots keeps the older scheme for A/B runs: up to FB_BATCH_SLOTS (default 8) independent
+  // proves in flight, one host thread and one set of streams and workspaces per slot, all reading the same
+  // resident key.  Big keys fill the GPU on their own and are proved one after the other.
   ProvingKey* pk = reinterpret_cast<ProvingKey*>(pk_);
   Ctx* c0 = reinterpret_cast<Ctx*>(ctx);
   if (!pk || !c0) { set_error("fb_prove_batch: null handle"); return FB_ERR_ARG; }

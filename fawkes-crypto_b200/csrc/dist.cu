@@ -155,6 +155,10 @@ struct LocalWorld {
 struct LocalExchange : NttExchange {
   LocalWorld* w;
   int rank;
+  cudaStream_t side = nullptr;  // set: dist_h_pipeline takes its overlapped schedule (exchanges on this stream)
+  cudaEvent_t evs[12] = {};
+  cudaStream_t side_stream() override { return side; }
+  cudaEvent_t event(int i) override { return evs[i]; }
   int all_to_all(const Fr* const* send, Fr* const* recv, int narrays, uint64_t count, cudaStream_t st) override {
     cudaStreamSynchronize(st);          // my send buffers are final
     w->send[rank] = send;
@@ -225,41 +229,55 @@ int fb_test_dist_h(fb_ctx* ctx_, int log_n, int g, const uint64_t* a, const uint
   if (!dom.dist_supported(g)) { dom.destroy(); set_error("2^%d over 2^%d ranks is not supported", log_n, g); return FB_ERR_ARG; }
   const int G = 1 << g, kl = log_n - g;
   const uint64_t m = 1ull << log_n, ml = 1ull << kl;
-  LocalWorld world(G);
-  std::vector<std::thread> th;
-  std::vector<int> rcs(G, 0);
-  std::vector<Fr> result(m);
+  std::vector<Fr> result(m), result_ov(m);
   const uint64_t* src[3] = {a, b, c};
-  for (int r = 0; r < G; r++) {
-    th.emplace_back([&, r] {
-      cudaSetDevice(ctx->device);
-      cudaStream_t st;
-      cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
-      Fr *ev[3], *tmp[3];
-      std::vector<Fr> host(ml);
-      for (int v = 0; v < 3; v++) {
-        cudaMalloc(&ev[v], ml * sizeof(Fr));
-        cudaMalloc(&tmp[v], ml * sizeof(Fr));
-        for (uint64_t j = 0; j < ml; j++) memcpy(&host[j], src[v] + 4 * ((j << g) | (uint64_t)r), 32);  // cyclic
-        cudaMemcpyAsync(ev[v], host.data(), ml * sizeof(Fr), cudaMemcpyHostToDevice, st);
+  // both schedules of dist_h_pipeline: exchanges on the compute stream, then on a side stream under the transforms
+  for (int overlap = 0; overlap < 2; overlap++) {
+    LocalWorld world(G);
+    std::vector<std::thread> th;
+    std::vector<int> rcs(G, 0);
+    std::vector<Fr>& res = overlap ? result_ov : result;
+    for (int r = 0; r < G; r++) {
+      th.emplace_back([&, r] {
+        cudaSetDevice(ctx->device);
+        cudaStream_t st;
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        Fr *ev[3], *tmp[3];
+        std::vector<Fr> host(ml);
+        for (int v = 0; v < 3; v++) {
+          cudaMalloc(&ev[v], ml * sizeof(Fr));
+          cudaMalloc(&tmp[v], ml * sizeof(Fr));
+          for (uint64_t j = 0; j < ml; j++) memcpy(&host[j], src[v] + 4 * ((j << g) | (uint64_t)r), 32);  // cyclic
+          cudaMemcpyAsync(ev[v], host.data(), ml * sizeof(Fr), cudaMemcpyHostToDevice, st);
+          cudaStreamSynchronize(st);
+        }
+        LocalExchange x;
+        x.w = &world;
+        x.rank = r;
+        if (overlap) {
+          cudaStreamCreateWithFlags(&x.side, cudaStreamNonBlocking);
+          for (auto& e : x.evs) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        }
+        rcs[r] = dom.dist_h_pipeline(ev, tmp, g, r, &x, st);
         cudaStreamSynchronize(st);
-      }
-      LocalExchange x;
-      x.w = &world;
-      x.rank = r;
-      rcs[r] = dom.dist_h_pipeline(ev, tmp, g, r, &x, st);
-      cudaStreamSynchronize(st);
-      if (cudaGetLastError() != cudaSuccess) rcs[r] = -9;
-      // block layout, bit-reversed coefficient order: global position r * ml + j
-      cudaMemcpy(result.data() + (uint64_t)r * ml, ev[0], ml * sizeof(Fr), cudaMemcpyDeviceToHost);
-      for (int v = 0; v < 3; v++) { cudaFree(ev[v]); cudaFree(tmp[v]); }
-      cudaStreamDestroy(st);
-    });
+        if (cudaGetLastError() != cudaSuccess) rcs[r] = -9;
+        // block layout, bit-reversed coefficient order: global position r * ml + j
+        cudaMemcpy(res.data() + (uint64_t)r * ml, ev[0], ml * sizeof(Fr), cudaMemcpyDeviceToHost);
+        for (int v = 0; v < 3; v++) { cudaFree(ev[v]); cudaFree(tmp[v]); }
+        if (x.side) cudaStreamDestroy(x.side);
+        for (auto& e : x.evs) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(st);
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int r = 0; r < G; r++)
+      if (rcs[r]) { dom.destroy(); set_error("virtual rank %d failed (%d), overlap=%d", r, rcs[r], overlap); return FB_ERR_CUDA; }
   }
-  for (auto& t : th) t.join();
   dom.destroy();
-  for (int r = 0; r < G; r++)
-    if (rcs[r]) { set_error("virtual rank %d failed (%d)", r, rcs[r]); return FB_ERR_CUDA; }
+  if (memcmp(result.data(), result_ov.data(), m * sizeof(Fr)) != 0) {
+    set_error("the overlapped exchange schedule gives a different H");
+    return FB_ERR_CUDA;
+  }
   for (uint64_t p = 0; p < m; p++) {
     uint64_t i = 0;
     for (int bit = 0; bit < log_n; bit++) i |= ((p >> bit) & 1) << (log_n - 1 - bit);

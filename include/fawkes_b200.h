@@ -170,7 +170,9 @@ int fb_prove_timings(const fb_pk* pk, float ms[6]);
  * fb_dist_unique_id on rank 0 (NCCL unique id, 128 bytes), ship it to every rank, then fb_dist_init on
  * each.  A key loaded afterwards with fb_pk_load_shard(shard = rank, nshards = world) also shards the
  * R1CS rows and the H pipeline (four-step NTT, NCCL all-to-all over NVLink) when world is a power of
- * two and the domain is large enough; otherwise those stay replicated and only the MSMs shard. */
+ * two and the domain is large enough; otherwise those stay replicated and only the MSMs shard.
+ * The exchanges of the three evaluation arrays run on a side stream under the transforms of the next array
+ * (environment FB_DIST_NO_OVERLAP=1 at fb_dist_init time: one stream, for A/B runs). */
 int fb_dist_unique_id(uint8_t id[128]);
 int fb_dist_init(fb_ctx* ctx, int rank, int world, const uint8_t id[128]);
 
