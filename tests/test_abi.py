@@ -29,6 +29,56 @@ def test_library_exports_every_declared_symbol():
     assert names == set(fb.native.SIGNATURES), names ^ set(fb.native.SIGNATURES)
 
 
+def _split_params(arglist: str):
+    arglist = arglist.strip()
+    if arglist in ("", "void"):
+        return []
+    return [a.strip() for a in arglist.split(",")]
+
+
+def test_rust_sys_crate_follows_the_header():
+    """rust/fawkes-b200-sys cannot be compiled in this image (no Rust toolchain), so its extern block is checked
+    against include/fawkes_b200.h textually: every bound function is declared in the header with the same number
+    of arguments and the same return kind, the error codes and load flags carry the header's values, and every
+    product entry point (everything above the benchmark / self-test helpers) is bound."""
+    hdr = open(os.path.join(ROOT, "include", "fawkes_b200.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {}
+    for ret, name, args in re.findall(r"^\s*([A-Za-z_][\w \*]*?)\s*\b(fb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr_nc, flags=re.M):
+        decl[name] = (ret.strip(), _split_params(" ".join(args.split())))
+    rs = open(os.path.join(ROOT, "rust", "fawkes-b200-sys", "src", "lib.rs")).read()
+    rs_nc = re.sub(r"//.*", "", rs)
+    bound = {}
+    for name, args, ret in re.findall(r"pub fn (fb_[a-z0-9_]+)\s*\(([^)]*)\)\s*(->\s*[^;]+)?;", rs_nc):
+        bound[name] = (_split_params(" ".join(args.split())), ret.replace("->", "").strip())
+    assert len(bound) >= 30
+    for name, (args, ret) in bound.items():
+        assert name in decl, f"{name} is bound in Rust but not declared in the header"
+        cret, cargs = decl[name]
+        assert len(args) == len(cargs), f"{name}: {len(args)} arguments in Rust, {len(cargs)} in the header"
+        want = {"int": "c_int", "void": "", "const char*": "*const c_char", "uint64_t": "u64"}[cret.replace(" *", "*")]
+        assert ret == want, f"{name}: returns {ret!r} in Rust, {cret!r} in the header"
+        for ra, ca in zip(args, cargs):
+            is_ptr_c = "*" in ca or "[" in ca
+            is_ptr_rs = ra.split(":", 1)[1].strip().startswith("*")
+            assert is_ptr_c == is_ptr_rs, f"{name}: argument {ra!r} against {ca!r}"
+    # constants
+    for cname, val in re.findall(r"#define\s+(FB_(?:OK|ERR_[A-Z]+|LOAD_[A-Z_]+))\s+\(?(-?\d+)\)?", hdr):
+        m = re.search(rf"pub const {cname}: c_int = (-?\d+);", rs)
+        assert m and int(m.group(1)) == int(val), f"{cname} differs between the header and the Rust crate"
+    # the product surface: everything declared before the synthetic-circuit / instrumentation helpers
+    product = [n for n in decl if hdr_nc.index(n + "(") < hdr_nc.index("fb_circuit_synth(")]
+    missing = sorted(set(product) - set(bound) - {"fb_circuit_from_raw_gates_gpu"})
+    assert not missing, f"product entry points without a Rust binding: {missing}"
+    # fb_pk_info: same fields in the same order
+    c_fields = []
+    for ty, names in re.findall(r"\b(uint32_t|uint64_t)\s+([\w, ]+);",
+                                hdr_nc[hdr_nc.index("typedef struct fb_pk_info"):hdr_nc.index("} fb_pk_info;")]):
+        c_fields += [(n.strip(), ty[4:6]) for n in names.split(",")]
+    r_fields = re.findall(r"pub (\w+): u(32|64),", rs[rs.index("pub struct fb_pk_info"):rs.index('extern "C"')])
+    assert c_fields == r_fields, (c_fields, r_fields)
+
+
 def test_no_cpu_fallback_without_device():
     import fawkes_crypto_b200 as fb
     if fb.native.lib.fb_device_count() > 0:
