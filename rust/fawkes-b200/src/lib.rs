@@ -93,8 +93,13 @@ impl<'c> ProvingKey<'c> {
     }
     /// Multi-GPU: this process keeps base indices `[shard, shard + 1) * len / nshards` of every query.
     pub fn load_shard(ctx: &'c Context, p: &Parameters, shard: i32, nshards: i32) -> io::Result<Self> {
-        let flags = if p.checked { sys::FB_LOAD_CHECKED } else { 0 }
-            | if p.disallow_points_at_infinity { sys::FB_LOAD_NO_INFINITY } else { 0 };
+        let mut flags = 0;
+        if p.checked {
+            flags |= sys::FB_LOAD_CHECKED;
+        }
+        if p.disallow_points_at_infinity {
+            flags |= sys::FB_LOAD_NO_INFINITY;
+        }
         // n_in / n_aux are the ic / l query lengths of the bellman byte string (big-endian u32 counts)
         let (n_in, n_aux) = query_lengths(&p.bellman_bytes)?;
         let mut circ = ptr::null_mut();
