@@ -8,6 +8,7 @@
 #include <deque>
 #include <future>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <set>
 #include <thread>
@@ -831,13 +832,13 @@ extern "C" {
 
 const char* fb_last_error(void) { return fb::last_error_cstr(); }
 
-int fb_device_count(void) {
+int fb_device_count(void) try {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
-}
+} FB_ABI_CATCH_INT
 
-int fb_init(const int* devices, int ndev, fb_ctx** out) {
+int fb_init(const int* devices, int ndev, fb_ctx** out) try {
   if (!out || ndev != 1) {
     set_error("fb_init: exactly one device per context (one process per GPU)");
     return FB_ERR_ARG;
@@ -868,9 +869,9 @@ int fb_init(const int* devices, int ndev, fb_ctx** out) {
   }
   *out = reinterpret_cast<fb_ctx*>(c);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-void fb_shutdown(fb_ctx* ctx) {
+void fb_shutdown(fb_ctx* ctx) try {
   Ctx* c = reinterpret_cast<Ctx*>(ctx);
   if (!c) return;
   cudaSetDevice(c->device);
@@ -884,26 +885,25 @@ void fb_shutdown(fb_ctx* ctx) {
   cudaStreamDestroy(c->stream);
   for (int i = 0; i < 3; i++) { cudaStreamDestroy(c->aux[i]); cudaEventDestroy(c->aux_done[i]); }
   delete c;
-}
+} FB_ABI_CATCH_VOID
 
 void fb_free(void* p) { free(p); }
 
 int fb_circuit_from_raw_gates(const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
-                              uint32_t n_aux, fb_circuit** out) {
+                              uint32_t n_aux, fb_circuit** out) try {
   if (!out || (!gates && len)) { set_error("fb_circuit_from_raw_gates: bad argument"); return FB_ERR_ARG; }
-  Circuit* c = new Circuit();
+  std::unique_ptr<Circuit> c(new Circuit());  // freed on every error path, exceptions included
   c->n_in = n_in;
   c->n_aux = n_aux;
   int rc = parse_gates_to_csr(gates, len, n_in, n_aux, c->csr);
-  if (rc) { delete c; return rc; }
+  if (rc) return rc;
   if (c->csr.n_gates != num_gates) {
     set_error("gate stream holds %u gates, Parameters announce %u", c->csr.n_gates, num_gates);
-    delete c;
     return FB_ERR_FORMAT;
   }
-  *out = reinterpret_cast<fb_circuit*>(c);
+  *out = reinterpret_cast<fb_circuit*>(c.release());
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // Most bytes a gate stream announcing `num_gates` gates over n_in + n_aux variables can hold: three LCs per
 // gate, each a u32 count and at most one 37-byte term per variable (LCs are kept canonical, lc.rs:89-118);
@@ -916,44 +916,43 @@ static size_t gate_stream_cap(uint32_t num_gates, uint32_t n_in, uint32_t n_aux)
 }
 
 int fb_circuit_from_gates(const uint8_t* gates_brotli, size_t len, uint32_t num_gates, uint32_t n_in,
-                          uint32_t n_aux, fb_circuit** out) {
+                          uint32_t n_aux, fb_circuit** out) try {
   std::vector<uint8_t> raw;
   int rc = brotli_decode(gates_brotli, len, raw, gate_stream_cap(num_gates, n_in, n_aux));
   if (rc) return rc;
   return fb_circuit_from_raw_gates(raw.data(), raw.size(), num_gates, n_in, n_aux, out);
-}
+} FB_ABI_CATCH_INT
 
 int fb_circuit_from_raw_gates_gpu(fb_ctx* ctx, const uint8_t* gates, size_t len, uint32_t num_gates, uint32_t n_in,
-                                  uint32_t n_aux, fb_circuit** out, float* times_ms) {
+                                  uint32_t n_aux, fb_circuit** out, float* times_ms) try {
   if (!ctx || !out || (!gates && len)) { set_error("fb_circuit_from_raw_gates_gpu: bad argument"); return FB_ERR_ARG; }
-  Circuit* c = new Circuit();
+  std::unique_ptr<Circuit> c(new Circuit());  // freed on every error path, exceptions included
   c->n_in = n_in;
   c->n_aux = n_aux;
   int rc = parse_gates_device(reinterpret_cast<Ctx*>(ctx), gates, len, n_in, n_aux, c->csr, times_ms);
-  if (rc) { delete c; return rc; }
+  if (rc) return rc;
   if (c->csr.n_gates != num_gates) {
     set_error("gate stream holds %u gates, Parameters announce %u", c->csr.n_gates, num_gates);
-    delete c;
     return FB_ERR_FORMAT;
   }
-  *out = reinterpret_cast<fb_circuit*>(c);
+  *out = reinterpret_cast<fb_circuit*>(c.release());
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 int fb_circuit_from_gates_gpu(fb_ctx* ctx, const uint8_t* gates_brotli, size_t len, uint32_t num_gates, uint32_t n_in,
-                              uint32_t n_aux, fb_circuit** out, float* times_ms) {
+                              uint32_t n_aux, fb_circuit** out, float* times_ms) try {
   std::vector<uint8_t> raw;
   auto t0 = std::chrono::steady_clock::now();
   int rc = brotli_decode(gates_brotli, len, raw, gate_stream_cap(num_gates, n_in, n_aux));
   if (rc) return rc;
   if (times_ms) times_ms[4] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return fb_circuit_from_raw_gates_gpu(ctx, raw.data(), raw.size(), num_gates, n_in, n_aux, out, times_ms);
-}
+} FB_ABI_CATCH_INT
 
 void fb_circuit_free(fb_circuit* c) { delete reinterpret_cast<Circuit*>(c); }
 
 int fb_circuit_shape(const fb_circuit* c_, uint32_t* n_in, uint32_t* n_aux, uint32_t* n_gates,
-                     uint64_t* nnz) {
+                     uint64_t* nnz) try {
   const Circuit* c = reinterpret_cast<const Circuit*>(c_);
   if (!c) return FB_ERR_ARG;
   if (n_in) *n_in = c->n_in;
@@ -961,22 +960,22 @@ int fb_circuit_shape(const fb_circuit* c_, uint32_t* n_in, uint32_t* n_aux, uint
   if (n_gates) *n_gates = c->csr.n_gates;
   if (nnz) *nnz = c->csr.col[0].size() + c->csr.col[1].size() + c->csr.col[2].size();
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 int fb_pk_load_shard(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
-                     const fb_circuit* circuit, int checked, int shard, int nshards, fb_pk** out) {
+                     const fb_circuit* circuit, int checked, int shard, int nshards, fb_pk** out) try {
   return load_key(reinterpret_cast<Ctx*>(ctx), bellman_params, len,
                   reinterpret_cast<const Circuit*>(circuit), checked, shard, nshards,
                   reinterpret_cast<ProvingKey**>(out));
-}
+} FB_ABI_CATCH_INT
 
 int fb_pk_load_circuit(fb_ctx* ctx, const uint8_t* bellman_params, size_t len,
-                       const fb_circuit* circuit, int checked, fb_pk** out) {
+                       const fb_circuit* circuit, int checked, fb_pk** out) try {
   return fb_pk_load_shard(ctx, bellman_params, len, circuit, checked, 0, 1, out);
-}
+} FB_ABI_CATCH_INT
 
 int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uint8_t* gates_brotli,
-               size_t glen, uint32_t num_gates, int checked, fb_pk** out) {
+               size_t glen, uint32_t num_gates, int checked, fb_pk** out) try {
   ParamsView v;
   int rc = parse_params(bellman_params, len, v);
   if (rc) return rc;
@@ -986,15 +985,15 @@ int fb_pk_load(fb_ctx* ctx, const uint8_t* bellman_params, size_t len, const uin
   rc = fb_pk_load_circuit(ctx, bellman_params, len, c, checked, out);
   fb_circuit_free(c);
   return rc;
-}
+} FB_ABI_CATCH_INT
 
-void fb_pk_free(fb_pk* pk) {
+void fb_pk_free(fb_pk* pk) try {
   ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
   if (p && p->ctx) cudaSetDevice(p->ctx->device);
   pk_release(p);
-}
+} FB_ABI_CATCH_VOID
 
-int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
+int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) try {
   const ProvingKey* pk = reinterpret_cast<const ProvingKey*>(pk_);
   if (!pk || !info) return FB_ERR_ARG;
   info->n_in = pk->n_in;
@@ -1019,7 +1018,7 @@ int fb_pk_get_info(const fb_pk* pk_, fb_pk_info* info) {
   info->reserved0 = 0;
   info->table_bytes = pk->table_bytes;
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // Sharded key on a distributed context (fb_dist_init + fb_pk_load_shard(rank, world)): a COLLECTIVE prove.  Every
 // rank calls with the same witness, r and s; each computes the partial sums of its base shard, the 640-byte
@@ -1069,7 +1068,7 @@ static int prove_collective(Ctx* ctx, ProvingKey* p, const uint64_t* inputs, uin
 
 int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux,
              uint32_t n_aux, const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256],
-             uint64_t* h_out) {
+             uint64_t* h_out) try {
   if (!inputs || (!aux && n_aux) || !r || !s || !proof_raw) { set_error("fb_prove: null buffer"); return FB_ERR_ARG; }
   ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
   if (p && p->nshards != 1) {
@@ -1079,7 +1078,7 @@ int fb_prove(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in, cons
   }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), p, inputs, n_in, aux, n_aux, nullptr, r, s,
                     proof_raw, nullptr, h_out);
-}
+} FB_ABI_CATCH_INT
 
 // A slot = everything one prove writes (witness, evaluations, MSM scratch, result buffers, events) plus its
 // own streams, next to a borrowed view of the key's immutable arrays.
@@ -1324,7 +1323,7 @@ extern "C" {
 
 int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* const* inputs, uint32_t n_in,
                    const uint64_t* const* aux, uint32_t n_aux, const uint64_t* r, const uint64_t* s,
-                   uint8_t* proofs_raw) {
+                   uint8_t* proofs_raw) try {
   if (!inputs || (!aux && n_aux) || !r || !s || !proofs_raw) { set_error("fb_prove_batch: null buffer"); return FB_ERR_ARG; }
   // The reference proves one circuit per prove() call (prover.rs:63-90); a batch is the same key used
   // `count` times.  Small keys (domain <= 2^16) go through prove_batched above: one set of launches per chunk of
@@ -1384,7 +1383,7 @@ int fb_prove_batch(fb_ctx* ctx, fb_pk* pk_, uint32_t count, const uint64_t* cons
   for (int t = 0; t < K; t++)
     if (rcs[t]) { set_error("%s", errs[t].c_str()); return rcs[t]; }
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // ---- streaming proves ------------------------------------------------
 // The reference's prove() is synchronous: witness generation (prover.rs:69-76, host, single thread) and
@@ -1505,7 +1504,7 @@ struct ProveStream {
   }
 };
 
-int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
+int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) try {
   ProvingKey* pk = reinterpret_cast<ProvingKey*>(pk_);
   Ctx* c0 = reinterpret_cast<Ctx*>(ctx);
   if (!pk || !c0 || !out) { set_error("fb_stream_open: null handle"); return FB_ERR_ARG; }
@@ -1548,10 +1547,10 @@ int fb_stream_open(fb_ctx* ctx, fb_pk* pk_, int depth, fb_stream** out) {
   else for (int t = 0; t < K; t++) st->workers.emplace_back([st, t] { st->run(t); });
   *out = reinterpret_cast<fb_stream*>(st);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 int fb_stream_submit(fb_stream* st_, const uint64_t* inputs, uint32_t n_in, const uint64_t* aux, uint32_t n_aux,
-                     const uint64_t r[4], const uint64_t s[4], uint64_t* ticket) {
+                     const uint64_t r[4], const uint64_t s[4], uint64_t* ticket) try {
   ProveStream* st = reinterpret_cast<ProveStream*>(st_);
   if (!st || !inputs || (!aux && n_aux) || !r || !s || !ticket) { set_error("fb_stream_submit: bad argument"); return FB_ERR_ARG; }
   if (n_in != st->pk->n_in || n_aux != st->pk->n_aux) {
@@ -1580,9 +1579,9 @@ int fb_stream_submit(fb_stream* st_, const uint64_t* inputs, uint32_t n_in, cons
   }
   st->cv_job.notify_one();
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_stream_wait(fb_stream* st_, uint64_t ticket, uint8_t proof_raw[256]) {
+int fb_stream_wait(fb_stream* st_, uint64_t ticket, uint8_t proof_raw[256]) try {
   ProveStream* st = reinterpret_cast<ProveStream*>(st_);
   if (!st || !proof_raw) { set_error("fb_stream_wait: bad argument"); return FB_ERR_ARG; }
   std::unique_lock<std::mutex> lk(st->mu);
@@ -1599,9 +1598,9 @@ int fb_stream_wait(fb_stream* st_, uint64_t ticket, uint8_t proof_raw[256]) {
   if (res.rc) { set_error("%s", res.err.c_str()); return res.rc; }
   memcpy(proof_raw, res.proof, 256);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-void fb_stream_close(fb_stream* st_) {
+void fb_stream_close(fb_stream* st_) try {
   ProveStream* st = reinterpret_cast<ProveStream*>(st_);
   if (!st) return;
   {
@@ -1628,10 +1627,10 @@ void fb_stream_close(fb_stream* st_) {
   }
   for (uint64_t* b : st->bufs) cudaFreeHost(b);
   delete st;
-}
+} FB_ABI_CATCH_VOID
 
 int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[4],
-                    const uint64_t s[4], uint8_t proof_raw[256]) {
+                    const uint64_t s[4], uint8_t proof_raw[256]) try {
   if (!dev_w || !r || !s || !proof_raw) { set_error("fb_prove_device: null buffer"); return FB_ERR_ARG; }
   ProvingKey* p = reinterpret_cast<ProvingKey*>(pk);
   if (p && p->nshards != 1) {  // collective, see fb_prove: every rank passes its own device copy of the witness
@@ -1640,17 +1639,17 @@ int fb_prove_device(fb_ctx* ctx, fb_pk* pk, const void* dev_w, const uint64_t r[
   }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), p, nullptr, 0, nullptr, 0, dev_w, r, s, proof_raw,
                     nullptr, nullptr);
-}
+} FB_ABI_CATCH_INT
 
 int fb_prove_partial(fb_ctx* ctx, fb_pk* pk, const uint64_t* inputs, uint32_t n_in,
-                     const uint64_t* aux, uint32_t n_aux, uint8_t partial[640]) {
+                     const uint64_t* aux, uint32_t n_aux, uint8_t partial[640]) try {
   if (!inputs || (!aux && n_aux) || !partial) { set_error("fb_prove_partial: null buffer"); return FB_ERR_ARG; }
   return prove_impl(reinterpret_cast<Ctx*>(ctx), reinterpret_cast<ProvingKey*>(pk), inputs, n_in, aux,
                     n_aux, nullptr, nullptr, nullptr, nullptr, partial, nullptr);
-}
+} FB_ABI_CATCH_INT
 
 int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* partials, int nparts,
-                    const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]) {
+                    const uint64_t r[4], const uint64_t s[4], uint8_t proof_raw[256]) try {
   if (!bellman_params || !partials || nparts < 1 || !r || !s || !proof_raw) { set_error("fb_prove_finish: bad argument"); return FB_ERR_ARG; }
   ParamsView v;
   int rc = parse_params(bellman_params, len < 580 ? len : 580, v);
@@ -1677,10 +1676,10 @@ int fb_prove_finish(const uint8_t* bellman_params, size_t len, const uint8_t* pa
     sum2 = add(sum2, h2_from(q));
   }
   return assemble(&vk, sum[0], sum[1], sum[2], sum[3], sum2, r, s, proof_raw);
-}
+} FB_ABI_CATCH_INT
 
 int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const uint32_t** col,
-                   const uint32_t** cidx, uint64_t* nnz, const uint64_t** coef_table, uint64_t* ncoef) {
+                   const uint32_t** cidx, uint64_t* nnz, const uint64_t** coef_table, uint64_t* ncoef) try {
   const Circuit* c = reinterpret_cast<const Circuit*>(c_);
   if (!c || m < 0 || m > 2) return FB_ERR_ARG;
   if (rowptr) *rowptr = c->csr.rowptr[m].data();
@@ -1690,7 +1689,7 @@ int fb_circuit_csr(const fb_circuit* c_, int m, const uint32_t** rowptr, const u
   if (coef_table) *coef_table = reinterpret_cast<const uint64_t*>(c->csr.coef.data());
   if (ncoef) *ncoef = c->csr.coef.size();
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 uint64_t fb_launch_count(void) { return fb::g_launches; }
 void fb_set_serial(int on) { fb::g_serial = on != 0; }
@@ -1698,18 +1697,18 @@ void fb_set_msm_tables(int mode) { fb::g_msm_tables = mode < 0 ? -1 : (mode ? 1 
 void fb_set_prove_graph(int on) { fb::g_prove_graph.store(on ? 1 : 0); }
 void fb_kernel_stats_enable(int on) { fb::kstat_enable(on != 0); }
 void fb_kernel_stats_reset(void) { fb::kstat_reset(); }
-int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) {
+int fb_kernel_stats(int which, uint64_t* launches, double* total_ms) try {
   if (which < 0 || which >= KSTAT_KINDS) return FB_ERR_ARG;
   unsigned long long n = 0;
   fb::kstat_collect(which, &n, total_ms);
   if (launches) *launches = n;
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_prove_timings(const fb_pk* pk, float ms[6]) {
+int fb_prove_timings(const fb_pk* pk, float ms[6]) try {
   if (!pk || !ms) return FB_ERR_ARG;
   for (int i = 0; i < 6; i++) ms[i] = g_timing.ms[i];
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 }  // extern "C"

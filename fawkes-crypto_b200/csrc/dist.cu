@@ -179,7 +179,7 @@ using namespace fb;
 
 extern "C" {
 
-int fb_dist_unique_id(uint8_t id[128]) {
+int fb_dist_unique_id(uint8_t id[128]) try {
   if (!id) return FB_ERR_ARG;
   NcclApi& n = nccl();
   if (!n.ok) { set_error("libnccl.so.2 not available"); return FB_ERR_CUDA; }
@@ -188,9 +188,9 @@ int fb_dist_unique_id(uint8_t id[128]) {
   if (rc) { set_error("ncclGetUniqueId: %s", n.GetErrorString(rc)); return FB_ERR_CUDA; }
   memcpy(id, u.internal, 128);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) {
+int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !id || world < 1 || rank < 0 || rank >= world) { set_error("fb_dist_init: bad argument"); return FB_ERR_ARG; }
   NcclApi& n = nccl();
@@ -213,13 +213,13 @@ int fb_dist_init(fb_ctx* ctx_, int rank, int world, const uint8_t id[128]) {
   ctx->rank = rank;
   ctx->world = world;
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // One-GPU check of the distributed H pipeline: 2^g virtual ranks (host threads, own streams) with the
 // exchange done by device-to-device copies.  a, b, c: row evaluations [2^log_n][4]; out: H
 // coefficients [2^log_n - 1][4] in natural order.
 int fb_test_dist_h(fb_ctx* ctx_, int log_n, int g, const uint64_t* a, const uint64_t* b, const uint64_t* c,
-                   uint64_t* out) {
+                   uint64_t* out) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !a || !b || !c || !out) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -284,6 +284,6 @@ int fb_test_dist_h(fb_ctx* ctx_, int log_n, int g, const uint64_t* a, const uint
     if (i < m - 1) memcpy(out + 4 * i, &result[p], 32);
   }
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 }  // extern "C"

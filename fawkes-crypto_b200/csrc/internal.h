@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -35,6 +36,22 @@ void kstat_end(int kind, cudaStream_t st);
       return FB_ERR_CUDA;                                                      \
     }                                                                              \
   } while (0)
+
+// Every entry point of the C ABI is a function-try-block closed by one of these: a C++ exception of the host code
+// (std::bad_alloc while parsing a multi-GB gate stream, std::system_error from thread creation) must not unwind
+// into the caller's frames -- for the Rust shim that is undefined behaviour.  The caller sees FB_ERR_HOST.
+#define FB_ABI_CATCH_INT                                                   \
+  catch (const std::exception& e) {                                        \
+    fb::set_error("host exception: %s", e.what());                         \
+    return FB_ERR_HOST;                                                    \
+  }                                                                        \
+  catch (...) {                                                            \
+    fb::set_error("unknown host exception");                               \
+    return FB_ERR_HOST;                                                    \
+  }
+#define FB_ABI_CATCH_VOID \
+  catch (...) {           \
+  }
 
 // R1CS in CSR form over the concatenated variable vector w = [inputs | aux].
 struct HostCsr {

@@ -196,7 +196,7 @@ using namespace fb;
 extern "C" {
 
 int fb_test_field(fb_ctx* ctx_, int field, int op, const uint64_t* a, const uint64_t* b,
-                  uint64_t* out, uint64_t n) {
+                  uint64_t* out, uint64_t n) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !a || !out) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -218,9 +218,9 @@ int fb_test_field(fb_ctx* ctx_, int field, int op, const uint64_t* a, const uint
   FB_CUDA(cudaGetLastError());
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_test_ntt(fb_ctx* ctx_, int log_n, int kind, uint64_t* data) {
+int fb_test_ntt(fb_ctx* ctx_, int log_n, int kind, uint64_t* data) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !data || kind < 0 || kind > 3) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -238,10 +238,10 @@ int fb_test_ntt(fb_ctx* ctx_, int log_n, int kind, uint64_t* data) {
   cudaFree(x); cudaFree(scratch);
   dom.destroy();
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 int fb_test_h(fb_ctx* ctx_, int log_n, const uint64_t* a, const uint64_t* b, const uint64_t* c,
-              uint64_t* out, float* ms) {
+              uint64_t* out, float* ms) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !a || !b || !c) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -282,10 +282,10 @@ int fb_test_h(fb_ctx* ctx_, int log_n, const uint64_t* a, const uint64_t* b, con
   cudaEventDestroy(e1);
   dom.destroy();
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_t* scalars,
-                uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep) {
+                uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !bases_raw || !scalars || !result_raw || (group != 1 && group != 2) || n == 0 ||
       n >= (1ull << 31))
@@ -346,9 +346,9 @@ int fb_test_msm(fb_ctx* ctx_, int group, const uint8_t* bases_raw, const uint64_
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) {
+int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !mac_per_s) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -374,11 +374,11 @@ int fb_probe_imad(fb_ctx* ctx_, double* mac_per_s) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // which: 0 carry-chained wide MAC rate (MAC/s), 1 mul_ptx rate, 2 mul_c rate (mul/s);
 // threads per block and blocks per SM selectable to see the occupancy dependence
-int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, double* per_s) {
+int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, double* per_s) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !per_s) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -414,19 +414,19 @@ int fb_probe_rate(fb_ctx* ctx_, int which, int threads, int blocks_per_sm, doubl
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 // Host only: the Pippenger plan MsmPlan::make picks for n points (window bits, digits per scalar, log2 entries per
 // accumulation task) with or without window tables -- lets the CPU tests pin the plans of the benchmark sizes.
-int fb_test_msm_plan(uint32_t n, int table, int* c, int* W, int* task_log) {
+int fb_test_msm_plan(uint32_t n, int table, int* c, int* W, int* task_log) try {
   const MsmPlan p = MsmPlan::make(n, table != 0);
   if (c) *c = p.c;
   if (W) *W = p.W;
   if (task_log) *task_log = p.task_log;
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_probe_fr_mul(fb_ctx* ctx_, double* mul_per_s) {
+int fb_probe_fr_mul(fb_ctx* ctx_, double* mul_per_s) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !mul_per_s) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -452,6 +452,6 @@ int fb_probe_fr_mul(fb_ctx* ctx_, double* mul_per_s) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 }  // extern "C"

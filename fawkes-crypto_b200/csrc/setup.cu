@@ -192,7 +192,7 @@ using namespace fb;
 
 extern "C" {
 
-int fb_test_fixed_base(fb_ctx* ctx_, int group, const uint64_t* scalars, uint64_t n, uint8_t* out_raw) {
+int fb_test_fixed_base(fb_ctx* ctx_, int group, const uint64_t* scalars, uint64_t n, uint8_t* out_raw) try {
   Ctx* ctx = reinterpret_cast<Ctx*>(ctx_);
   if (!ctx || !scalars || !out_raw || (group != 1 && group != 2)) return FB_ERR_ARG;
   FB_CUDA(cudaSetDevice(ctx->device));
@@ -201,7 +201,7 @@ int fb_test_fixed_base(fb_ctx* ctx_, int group, const uint64_t* scalars, uint64_
   if (!rc) rc = fbk.run(group, reinterpret_cast<const Fr*>(scalars), n, out_raw, 0);
   fbk.release();
   return rc;
-}
+} FB_ABI_CATCH_INT
 
 // shard / nshards: nshards == 1 generates every point.  Otherwise only the points fb_pk_load_shard(shard, nshards)
 // on this context keeps are generated (contiguous slices of l, a, b_g1, b_g2; for h the bit-reversed positions of
@@ -375,13 +375,13 @@ static int setup_impl(fb_ctx* ctx_, const fb_circuit* circuit, const uint64_t tr
 }
 
 int fb_setup(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4], uint8_t** params_out,
-             size_t* len_out) {
+             size_t* len_out) try {
   return setup_impl(ctx, circuit, trapdoor, 0, 1, params_out, len_out);
-}
+} FB_ABI_CATCH_INT
 
 int fb_setup_shard(fb_ctx* ctx, const fb_circuit* circuit, const uint64_t trapdoor[5][4], int shard, int nshards,
-                   uint8_t** params_out, size_t* len_out) {
+                   uint8_t** params_out, size_t* len_out) try {
   return setup_impl(ctx, circuit, trapdoor, shard, nshards, params_out, len_out);
-}
+} FB_ABI_CATCH_INT
 
 }  // extern "C"

@@ -10,6 +10,8 @@
 #include "../../include/fawkes_b200.h"
 
 #include "host_fr.h"
+#include <memory>
+
 #include "internal.h"
 
 namespace fb {
@@ -49,11 +51,11 @@ using namespace fb;
 
 extern "C" {
 
-int fb_circuit_synth(uint64_t n_rows, uint64_t seed, fb_circuit** out) {
+int fb_circuit_synth(uint64_t n_rows, uint64_t seed, fb_circuit** out) try {
   if (!out || n_rows < 3 || n_rows > (1ull << 27)) { set_error("fb_circuit_synth: bad size"); return FB_ERR_ARG; }
   SplitMix64 rng(seed);
   const uint32_t n_gates = (uint32_t)(n_rows - 2);
-  Circuit* c = new Circuit();
+  std::unique_ptr<Circuit> c(new Circuit());
   c->n_in = 2;
   std::vector<hfr::H> aux;
   aux.reserve(N_INIT_AUX + n_gates);
@@ -103,19 +105,19 @@ int fb_circuit_synth(uint64_t n_rows, uint64_t seed, fb_circuit** out) {
   c->inputs = {to_dev(inputs[0]), to_dev(inputs[1])};
   c->aux.resize(aux.size());
   memcpy(c->aux.data(), aux.data(), aux.size() * 32);
-  *out = reinterpret_cast<fb_circuit*>(c);
+  *out = reinterpret_cast<fb_circuit*>(c.release());
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_circuit_witness(const fb_circuit* c_, const uint64_t** inputs, const uint64_t** aux) {
+int fb_circuit_witness(const fb_circuit* c_, const uint64_t** inputs, const uint64_t** aux) try {
   const Circuit* c = reinterpret_cast<const Circuit*>(c_);
   if (!c || c->inputs.empty()) { set_error("circuit carries no witness"); return FB_ERR_ARG; }
   if (inputs) *inputs = reinterpret_cast<const uint64_t*>(c->inputs.data());
   if (aux) *aux = reinterpret_cast<const uint64_t*>(c->aux.data());
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
-int fb_synth_trapdoor(uint64_t seed, uint64_t out[7][4]) {
+int fb_synth_trapdoor(uint64_t seed, uint64_t out[7][4]) try {
   if (!out) return FB_ERR_ARG;
   SplitMix64 rng(seed ^ 0xB11D);
   for (int i = 0; i < 7; i++) {
@@ -123,6 +125,6 @@ int fb_synth_trapdoor(uint64_t seed, uint64_t out[7][4]) {
     memcpy(out[i], h.v, 32);
   }
   return FB_OK;
-}
+} FB_ABI_CATCH_INT
 
 }  // extern "C"

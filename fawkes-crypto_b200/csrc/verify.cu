@@ -154,7 +154,7 @@ F12 final_exp(const F12& f) {
 using namespace fb;
 
 extern "C" int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t proof_raw[256],
-                         const uint64_t* inputs, uint32_t n_inputs, int* ok) {
+                         const uint64_t* inputs, uint32_t n_inputs, int* ok) try {
   if (!vk_raw || !proof_raw || !ok || (!inputs && n_inputs)) { set_error("fb_verify: bad argument"); return FB_ERR_ARG; }
   *ok = 0;
   if (n_inputs + 1 != n_ic) {
@@ -233,4 +233,4 @@ extern "C" int fb_verify(const uint8_t* vk_raw, uint32_t n_ic, const uint8_t pro
   f = f12_mul(f, miller_loop(neg(alpha), beta));
   *ok = f12_eq(final_exp(f), f12_one()) ? 1 : 0;
   return FB_OK;
-}
+} FB_ABI_CATCH_INT

@@ -97,7 +97,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 FB_LOAD_CHECKED, FB_LOAD_NO_INFINITY = 1, 2
 
 ERR_NAMES = {0: "FB_OK", -1: "FB_ERR_ARG", -2: "FB_ERR_CUDA", -3: "FB_ERR_FORMAT", -4: "FB_ERR_DOMAIN",
-             -5: "FB_ERR_IDENTITY", -6: "FB_ERR_DENSITY", -7: "FB_ERR_VK"}
+             -5: "FB_ERR_IDENTITY", -6: "FB_ERR_DENSITY", -7: "FB_ERR_VK", -8: "FB_ERR_HOST"}
 
 
 class FbError(RuntimeError):

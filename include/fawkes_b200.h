@@ -54,6 +54,7 @@ extern "C" {
 #define FB_ERR_IDENTITY (-5) /* bellman SynthesisError::UnexpectedIdentity */
 #define FB_ERR_DENSITY (-6)  /* query length != structural density of the circuit */
 #define FB_ERR_VK (-7)       /* bellman SynthesisError::MalformedVerifyingKey */
+#define FB_ERR_HOST (-8)     /* a host-side C++ exception (out of memory, thread creation) stopped at the ABI */
 
 typedef struct fb_ctx fb_ctx;         /* one device + its streams */
 typedef struct fb_pk fb_pk;           /* HBM-resident proving key + CSR + workspaces */

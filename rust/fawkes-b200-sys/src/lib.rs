@@ -14,6 +14,7 @@ pub const FB_ERR_DOMAIN: c_int = -4; // SynthesisError::PolynomialDegreeTooLarge
 pub const FB_ERR_IDENTITY: c_int = -5; // SynthesisError::UnexpectedIdentity
 pub const FB_ERR_DENSITY: c_int = -6;
 pub const FB_ERR_VK: c_int = -7; // SynthesisError::MalformedVerifyingKey
+pub const FB_ERR_HOST: c_int = -8; // host-side C++ exception stopped at the ABI (out of memory)
 
 /// bits of the `checked` argument of `fb_pk_load*`: the two booleans of
 /// `Parameters::read(reader, disallow_points_at_infinity, checked)` (mod.rs:159)

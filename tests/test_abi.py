@@ -79,6 +79,27 @@ def test_rust_sys_crate_follows_the_header():
     assert c_fields == r_fields, (c_fields, r_fields)
 
 
+def test_host_exceptions_stop_at_the_abi():
+    """A std::bad_alloc inside the library (here: a 2^27-row synthetic circuit under a 6 GiB address-space limit) must
+    come back as FB_ERR_HOST with a message, not unwind through the C ABI (abort / undefined behaviour in a Rust
+    caller).  Runs in a child process because of the rlimit."""
+    import subprocess
+    import sys
+    code = (
+        "import resource, ctypes, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import fawkes_crypto_b200 as fb\n"
+        "resource.setrlimit(resource.RLIMIT_AS, (6 << 30, 6 << 30))\n"
+        "out = ctypes.c_void_p()\n"
+        "rc = fb.native.lib.fb_circuit_synth(1 << 27, 1, ctypes.byref(out))\n"
+        "print(rc, fb.native.lib.fb_last_error().decode())\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rc, msg = r.stdout.strip().split(" ", 1)
+    assert int(rc) == -8 and "host exception" in msg and "bad_alloc" in msg, r.stdout
+
+
 def test_no_cpu_fallback_without_device():
     import fawkes_crypto_b200 as fb
     if fb.native.lib.fb_device_count() > 0:
