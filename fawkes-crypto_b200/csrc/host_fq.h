@@ -7,6 +7,13 @@
 #include <cstdint>
 #include <cstring>
 
+#if !defined(__CUDA_ARCH__) && defined(__x86_64__)
+#include <immintrin.h>
+#define FB_HFQ_X86 1
+#else
+#define FB_HFQ_X86 0
+#endif
+
 #include "ff.cuh"
 
 namespace fb {
@@ -29,8 +36,23 @@ struct HFq {
 
 namespace hfq_detail {
 typedef unsigned __int128 u128;
+typedef unsigned long long ull;
 FB_HD constexpr uint64_t modl(int i) { constexpr uint64_t m[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull}; return m[i]; }
 constexpr uint64_t INV = 0x87d20782e4866389ull;
+#if FB_HFQ_X86
+// r in [0, 2p) -> [0, p): subtract p, keep the difference unless it borrowed (cmov, no branch)
+inline void reduce_once(ull& r0, ull& r1, ull& r2, ull& r3) {
+  ull t0, t1, t2, t3;
+  unsigned char bw = _subborrow_u64(0, r0, modl(0), &t0);
+  bw = _subborrow_u64(bw, r1, modl(1), &t1);
+  bw = _subborrow_u64(bw, r2, modl(2), &t2);
+  bw = _subborrow_u64(bw, r3, modl(3), &t3);
+  r0 = bw ? r0 : t0;
+  r1 = bw ? r1 : t1;
+  r2 = bw ? r2 : t2;
+  r3 = bw ? r3 : t3;
+}
+#else
 FB_HD bool geq(const uint64_t* a) {
   for (int i = 3; i >= 0; i--) {
     if (a[i] > modl(i)) return true;
@@ -46,8 +68,67 @@ FB_HD void subm(uint64_t* a) {
     bw = (uint64_t)(d >> 64) & 1;
   }
 }
+#endif
 }  // namespace hfq_detail
 
+#if FB_HFQ_X86
+// x86-64 host build: add/adc and sub/sbb chains through the carry intrinsics, a fully unrolled Montgomery product
+// (CIOS without the extra carry word: p < 2^254).  The tower arithmetic of the pairing (verify.cu) is dominated by
+// additions; the portable loops below compile to 4x slower code for them.
+FB_HD HFq add(const HFq& a, const HFq& b) {
+  using namespace hfq_detail;
+  ull r0, r1, r2, r3;
+  unsigned char c = _addcarry_u64(0, a.v[0], b.v[0], &r0);
+  c = _addcarry_u64(c, a.v[1], b.v[1], &r1);
+  c = _addcarry_u64(c, a.v[2], b.v[2], &r2);
+  c = _addcarry_u64(c, a.v[3], b.v[3], &r3);  // no carry out: 2p < 2^255
+  reduce_once(r0, r1, r2, r3);
+  HFq r;
+  r.v[0] = r0; r.v[1] = r1; r.v[2] = r2; r.v[3] = r3;
+  return r;
+}
+FB_HD HFq sub(const HFq& a, const HFq& b) {
+  using namespace hfq_detail;
+  ull r0, r1, r2, r3;
+  unsigned char bw = _subborrow_u64(0, a.v[0], b.v[0], &r0);
+  bw = _subborrow_u64(bw, a.v[1], b.v[1], &r1);
+  bw = _subborrow_u64(bw, a.v[2], b.v[2], &r2);
+  bw = _subborrow_u64(bw, a.v[3], b.v[3], &r3);
+  const ull m = 0 - (ull)bw;  // add p back when the difference went negative
+  unsigned char c = _addcarry_u64(0, r0, modl(0) & m, &r0);
+  c = _addcarry_u64(c, r1, modl(1) & m, &r1);
+  c = _addcarry_u64(c, r2, modl(2) & m, &r2);
+  c = _addcarry_u64(c, r3, modl(3) & m, &r3);
+  HFq r;
+  r.v[0] = r0; r.v[1] = r1; r.v[2] = r2; r.v[3] = r3;
+  return r;
+}
+FB_HD HFq mul(const HFq& a, const HFq& b) {
+  using namespace hfq_detail;
+  ull t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define FB_HFQ_ROUND(bi)                                                         \
+  {                                                                              \
+    u128 x = (u128)a.v[0] * (bi) + t0;                                           \
+    ull A = (ull)(x >> 64);                                                      \
+    const ull m = (ull)x * INV;                                                  \
+    u128 y = (u128)m * modl(0) + (ull)x;                                         \
+    ull C = (ull)(y >> 64);                                                      \
+    x = (u128)a.v[1] * (bi) + t1 + A; A = (ull)(x >> 64);                        \
+    y = (u128)m * modl(1) + (ull)x + C; C = (ull)(y >> 64); t0 = (ull)y;         \
+    x = (u128)a.v[2] * (bi) + t2 + A; A = (ull)(x >> 64);                        \
+    y = (u128)m * modl(2) + (ull)x + C; C = (ull)(y >> 64); t1 = (ull)y;         \
+    x = (u128)a.v[3] * (bi) + t3 + A; A = (ull)(x >> 64);                        \
+    y = (u128)m * modl(3) + (ull)x + C; C = (ull)(y >> 64); t2 = (ull)y;         \
+    t3 = C + A;                                                                  \
+  }
+  FB_HFQ_ROUND(b.v[0]) FB_HFQ_ROUND(b.v[1]) FB_HFQ_ROUND(b.v[2]) FB_HFQ_ROUND(b.v[3])
+#undef FB_HFQ_ROUND
+  reduce_once(t0, t1, t2, t3);  // the Montgomery product of two reduced operands is < 2p
+  HFq r;
+  r.v[0] = t0; r.v[1] = t1; r.v[2] = t2; r.v[3] = t3;
+  return r;
+}
+#else
 FB_HD HFq add(const HFq& a, const HFq& b) {
   using namespace hfq_detail;
   HFq r;
@@ -92,10 +173,11 @@ FB_HD HFq mul(const HFq& a, const HFq& b) {
   if (geq(r.v)) subm(r.v);
   return r;
 }
+#endif
 FB_HD HFq sqr(const HFq& a) { return mul(a, a); }
 FB_HD HFq dbl(const HFq& a) { return add(a, a); }
 FB_HD HFq neg(const HFq& a) { return sub(HFq::zero(), a); }
-FB_HD HFq inv(const HFq& a) {  // a^(p-2)
+FB_HD HFq inv_fermat(const HFq& a) {  // a^(p-2); the yardstick of inv() in fb_test_pairing
   using namespace hfq_detail;
   const uint64_t e[4] = {modl(0) - 2, modl(1), modl(2), modl(3)};
   HFq r = HFq::one();
@@ -104,6 +186,59 @@ FB_HD HFq inv(const HFq& a) {  // a^(p-2)
     if ((e[i >> 6] >> (i & 63)) & 1) r = mul(r, a);
   }
   return r;
+}
+// Binary extended Euclid on the Montgomery residue (Hankerson et al., Alg. 2.22): 2.4x faster than a^(p-2) on
+// the host (no multiplications, ~380 shift / subtract steps).  The input aR gives (aR)^-1; one Montgomery product
+// with R^3 turns that into a^-1 R.  inv(0) = 0, as with Fermat.
+FB_HD HFq inv(const HFq& a) {
+  using namespace hfq_detail;
+  if (a.is_zero()) return a;
+  uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) { u[i] = a.v[i]; v[i] = modl(i); }
+  auto is_one = [](const uint64_t* x) { return x[0] == 1 && (x[1] | x[2] | x[3]) == 0; };
+  auto shr1 = [](uint64_t* x) {
+    x[0] = (x[0] >> 1) | (x[1] << 63);
+    x[1] = (x[1] >> 1) | (x[2] << 63);
+    x[2] = (x[2] >> 1) | (x[3] << 63);
+    x[3] >>= 1;
+  };
+  auto half_mod = [&](uint64_t* x) {  // x / 2 mod p for x < p (x + p < 2^255)
+    if (x[0] & 1) {
+      u128 c = 0;
+      for (int i = 0; i < 4; i++) { c += (u128)x[i] + modl(i); x[i] = (uint64_t)c; c >>= 64; }
+    }
+    shr1(x);
+  };
+  auto geq_ = [](const uint64_t* x, const uint64_t* y) {
+    for (int i = 3; i >= 0; i--)
+      if (x[i] != y[i]) return x[i] > y[i];
+    return true;
+  };
+  auto sub_ = [](uint64_t* x, const uint64_t* y) {  // x -= y, returns the borrow
+    uint64_t bw = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)x[i] - y[i] - bw;
+      x[i] = (uint64_t)d;
+      bw = (uint64_t)(d >> 64) & 1;
+    }
+    return bw;
+  };
+  auto sub_mod = [&](uint64_t* x, const uint64_t* y) {
+    if (sub_(x, y)) {
+      u128 c = 0;
+      for (int i = 0; i < 4; i++) { c += (u128)x[i] + modl(i); x[i] = (uint64_t)c; c >>= 64; }
+    }
+  };
+  while (!is_one(u) && !is_one(v)) {
+    while (!(u[0] & 1)) { shr1(u); half_mod(x1); }
+    while (!(v[0] & 1)) { shr1(v); half_mod(x2); }
+    if (geq_(u, v)) { sub_(u, v); sub_mod(x1, x2); }
+    else { sub_(v, u); sub_mod(x2, x1); }
+  }
+  HFq y, r3;
+  const uint64_t R3[4] = {0xb1cd6dafda1530dfull, 0x62f210e6a7283db6ull, 0xef7f0b0c0ada0afbull, 0x20fd6e902d592544ull};  // R^3 mod p
+  for (int i = 0; i < 4; i++) { y.v[i] = is_one(u) ? x1[i] : x2[i]; r3.v[i] = R3[i]; }
+  return mul(y, r3);
 }
 
 struct HFq2 {

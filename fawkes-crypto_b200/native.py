@@ -84,6 +84,7 @@ SIGNATURES = {
     "fb_dist_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "fb_test_msm": (C.c_int, [vp, C.c_int, vp, vp, C.c_uint64, vp, C.c_int, f32p]),
     "fb_test_msm_plan": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "fb_test_pairing": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_int)]),
     "fb_test_fixed_base": (C.c_int, [vp, C.c_int, vp, C.c_uint64, vp]),
     "fb_probe_imad": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "fb_probe_rate": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),

@@ -237,6 +237,9 @@ int fb_test_msm(fb_ctx* ctx, int group, const uint8_t* bases_raw, const uint64_t
                 uint64_t n, uint8_t* result_raw, int reps, float* ms_per_rep);
 /* host only: window bits, digits per scalar and log2(entries per accumulation task) MsmPlan::make picks for n points */
 int fb_test_msm_plan(uint32_t n, int table, int* c, int* W, int* task_log);
+/* host pairing self-check (no device): addition-chain final exponentiation == plain square-and-multiply, bilinearity
+ * e(aG1, bG2) == e(G1, G2)^(ab), multi-pair loop e(P,Q) e(-P,Q) == 1; n rounds from a seeded stream */
+int fb_test_pairing(uint64_t seed, int n, int* failures);
 /* bases[i] = k_i * G (fixed-base kernel used by setup), raw affine out */
 int fb_test_fixed_base(fb_ctx* ctx, int group, const uint64_t* scalars, uint64_t n,
                        uint8_t* out_raw);

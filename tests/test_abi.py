@@ -100,6 +100,37 @@ def test_host_exceptions_stop_at_the_abi():
     assert int(rc) == -8 and "host exception" in msg and "bad_alloc" in msg, r.stdout
 
 
+def test_host_pairing_self_check():
+    """fb_verify's pairing runs on the host (verifier.rs:75-81 is host code in the reference too).  The library's
+    self-check compares, on seeded random values: the binary-Euclid field inverse with a^(p-2); the addition-chain
+    final exponentiation with plain square-and-multiply over (p^4 - p^2 + 1)/r; e(aG1, bG2) with e(G1, G2)^(ab); and
+    the shared-squaring multi-pair loop on e(P, Q) e(-P, Q) = 1."""
+    import fawkes_crypto_b200 as fb
+    bad = C.c_int(-1)
+    fb.native.check(fb.native.lib.fb_test_pairing(20261017, 6, C.byref(bad)))
+    assert bad.value == 0
+
+
+def test_final_exponentiation_chain_is_the_exact_exponent():
+    """The exponent identity behind verify.cu: final_exp -- with conjugation = -1 and Frobenius = *p on exponents,
+    the chain y0 y1^2 y2^6 y3^12 y4^18 y5^30 y6^36 is EXACTLY (p^4 - p^2 + 1)/r, and that is HARD_EXP."""
+    p, r, x = bn.P, bn.R, 4965661367192848881
+    assert p == 36 * x**4 + 36 * x**3 + 24 * x**2 + 6 * x + 1 and r == 36 * x**4 + 36 * x**3 + 18 * x**2 + 6 * x + 1
+    e = (p**4 - p**2 + 1) // r
+    src = open(os.path.join(ROOT, "fawkes-crypto_b200", "csrc", "verify_consts.h")).read()
+    limbs = re.search(r"HARD_EXP\[24\] = \{([^}]*)\}", src).group(1)
+    assert sum(int(v.strip().rstrip("u"), 16) << (32 * i) for i, v in enumerate(limbs.split(","))) == e
+    y0 = p + p**2 + p**3
+    y1, y2, y3, y4, y5, y6 = -1, x**2 * p**2, -(x * p), -(x + x**2 * p), -(x**2), -(x**3 + x**3 * p)
+    t0 = 2 * y6 + y4 + y5
+    t1 = y3 + y5 + t0
+    t0 = t0 + y2
+    t1 = 2 * (2 * t1 + t0)
+    t0 = t1 + y1
+    t1 = t1 + y0
+    assert 2 * t0 + t1 == e
+
+
 def test_no_cpu_fallback_without_device():
     import fawkes_crypto_b200 as fb
     if fb.native.lib.fb_device_count() > 0:
