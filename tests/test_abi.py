@@ -131,6 +131,17 @@ def test_final_exponentiation_chain_is_the_exact_exponent():
     assert 2 * t0 + t1 == e
 
 
+def test_verify_constants_are_regenerated_from_the_curve_parameters():
+    """csrc/verify_consts.h (hard-part exponent, ate loop count, Frobenius constants) is exactly what
+    tools/gen_verify_consts.py derives from the BN parameter x."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_verify_consts", os.path.join(ROOT, "tools", "gen_verify_consts.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.P == bn.P and mod.R == bn.R
+    assert mod.header() == open(os.path.join(ROOT, "fawkes-crypto_b200", "csrc", "verify_consts.h")).read()
+
+
 def test_no_cpu_fallback_without_device():
     import fawkes_crypto_b200 as fb
     if fb.native.lib.fb_device_count() > 0:
