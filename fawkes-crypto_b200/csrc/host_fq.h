@@ -229,6 +229,11 @@ FB_HD HFq inv(const HFq& a) {
       for (int i = 0; i < 4; i++) { c += (u128)x[i] + modl(i); x[i] = (uint64_t)c; c >>= 64; }
     }
   };
+  // the loop needs 0 < u < p (gcd(u, p) = 1); every HFq in the library is reduced, but a limb pattern >= p must
+  // not hang the caller: bring it below p first (2^256 < 6p)
+  for (int k = 0; k < 6; k++)
+    if (geq_(u, v)) sub_(u, v);
+  if ((u[0] | u[1] | u[2] | u[3]) == 0) return HFq::zero();
   while (!is_one(u) && !is_one(v)) {
     while (!(u[0] & 1)) { shr1(u); half_mod(x1); }
     while (!(v[0] & 1)) { shr1(v); half_mod(x2); }
