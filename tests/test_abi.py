@@ -100,6 +100,52 @@ def test_host_exceptions_stop_at_the_abi():
     assert int(rc) == -8 and "host exception" in msg and "bad_alloc" in msg, r.stdout
 
 
+def test_host_verify_accepts_the_committed_golden_proofs():
+    """fb_verify needs no device, so the product's pairing is checked here against keys made by the CPU chain
+    (oracle/cpu_setup.cpp) and the committed golden proofs: the 2^12-row synthetic circuit and the two real circuits
+    (configs[0] Poseidon Merkle proof, configs[1] EdDSA-Poseidon, eight distinct signatures).  Three different
+    gamma / delta / ic sets; every proof is accepted, every proof with another statement's inputs is rejected."""
+    import hashlib
+    import bench
+    import fawkes_crypto_b200 as fb
+    from oracle import cpu
+
+    def vk_of(pbuf, n_in):
+        params = fb.Parameters(pbuf.array, 0, b"")
+        assert params.n_in == n_in
+        return params.get_vk()
+
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "synth_proofs.json")))["12"]
+    circ = cpu.Circuit.synthetic(1 << 12, g["seed"])
+    pbuf, _ = cpu.setup(circ, cpu.synth_trapdoor(g["seed"]), 4)
+    assert hashlib.sha256(pbuf.array).hexdigest() == g["params_sha256"]
+    vk = vk_of(pbuf, circ.n_in)
+    proof = fb.Proof.from_raw(bytes.fromhex(g["proof_raw_hex"]))
+    inputs = np.array(circ.inputs[1:], dtype=np.uint64)
+    assert fb.verify(vk, proof, inputs) is True
+    assert fb.verify(vk, proof, fr_np([12345])) is False
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bench_cfgs.npz"))
+    for cfg in ("cfg1", "cfg2"):
+        n_gates, n_in, n_aux = (int(v) for v in z[f"{cfg}_shape"])
+        c = fb.Circuit.from_gates_blob(z[f"{cfg}_gates_brotli"].tobytes(), n_gates, n_in, n_aux)
+        rp, cl, cf = bench.expand_csr(fb, c)
+        oc = cpu.Circuit.from_csr(n_gates, n_in, n_aux, rp, cl, cf)
+        pbuf, _ = cpu.setup(oc, z[f"{cfg}_trapdoor_r_s"], 4)
+        assert hashlib.sha256(pbuf.array).digest() == z[f"{cfg}_params_sha256"].tobytes()
+        vk = vk_of(pbuf, n_in)
+        if cfg == "cfg1":
+            cases = [(z["cfg1_proof"].tobytes(), z["cfg1_inputs"][1:])]
+        else:
+            cases = [(z["cfg2_proofs_first8"][i].tobytes(), z["cfg2_inputs"][i][1:]) for i in range(8)]
+        for i, (raw, ins) in enumerate(cases):
+            assert fb.verify(vk, fb.Proof.from_raw(raw), np.ascontiguousarray(ins)) is True, (cfg, i)
+        if len(cases) > 1:  # another signature's public input
+            assert fb.verify(vk, fb.Proof.from_raw(cases[0][0]), np.ascontiguousarray(cases[1][1])) is False
+        else:
+            assert fb.verify(vk, fb.Proof.from_raw(cases[0][0]), fr_np([7])) is False
+
+
 def test_host_pairing_self_check():
     """fb_verify's pairing runs on the host (verifier.rs:75-81 is host code in the reference too).  The library's
     self-check compares, on seeded random values: the binary-Euclid field inverse with a^(p-2); the addition-chain
